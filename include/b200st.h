@@ -1,0 +1,59 @@
+/* libb200st — C ABI of the B200-native SpeechTransformer hot path.
+ *
+ * Drop-in boundary for bytedance/neurst (reference @ /root/reference).  The reference is pure Python; its
+ * "FFI" for this path is the class registry (neurst/utils/registry.py:24-137) through which Trainer and the
+ * models reach neurst/layers/** and neurst/criterions/**.  Each entry point below replaces the TF/PyTorch
+ * library ops behind one reference function (file:line cited per function); INTEGRATION.md shows the
+ * ctypes binding a maintainer adds.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (weights, activations, workspace);
+ * every call is asynchronous on the given cudaStream_t (passed as void*); return 0 = ok, non-zero = error
+ * with a thread-local message from b200st_last_error(); no exceptions cross the ABI; the library never
+ * allocates device memory.  dtype codes: 0 = fp32, 1 = bf16.
+ */
+#ifndef B200ST_H_
+#define B200ST_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ST_F32 0
+#define B200ST_BF16 1
+
+const char* b200st_last_error(void);
+int b200st_version(void);
+/* number of hand-written kernels launched by this process so far (bench.py "gpu_launches") */
+int64_t b200st_launch_count(void);
+
+/* ---- generic contraction (tf.einsum / Dense / tf.matmul sites; neurst/layers/common_layers.py:270,276-288,
+ *      multi_head_attention.py:145,215; text_modalities.py:104-108) ---------------------------------------
+ * C[b2][b1][m][n] = epi(alpha * sum_k A(m,k) B(n,k)); operands K-major (mn_major=0) or MN-major (1).
+ * bf16 operands -> tcgen05/TMEM/TMA kernel; fp32 operands -> fp32 FMA kernel (parity mode). */
+typedef struct {
+  const void* ptr; int32_t dtype; int32_t mn_major; int64_t ld, sb1, sb2;
+} b200st_operand;
+typedef struct {
+  int32_t M, N, K, nb1, nb2;
+  b200st_operand A, B;
+  void* C; int32_t c_dtype; int64_t ldc, c_sb1, c_sb2;
+  float alpha;
+  const float* bias;
+  int32_t relu;
+  const void* mask_src; int32_t mask_dtype; int64_t mask_ld, mask_sb1, mask_sb2;
+  float dropout_p; uint64_t dropout_seed, dropout_stream;
+  const float* residual; int64_t res_ld, res_sb1, res_sb2;
+  int32_t accumulate;
+  int32_t splitk;        /* 1 = none, 0 = auto (linear fp32 accumulate epilogues only) */
+  int32_t force_simt;    /* tests: run the fp32-FMA kernel even on bf16 operands */
+} b200st_gemm_args;
+int b200st_gemm(const b200st_gemm_args* args, void* stream);
+
+/* tests only: override tcgen05 shared-memory descriptor fields / tile config (0 = default) */
+int b200st_debug_tc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t k_lbo, uint32_t k_sbo, int32_t force_bn,
+                    int32_t force_stages, int32_t max_ctas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ST_H_ */

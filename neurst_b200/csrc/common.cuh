@@ -1,0 +1,110 @@
+// Shared device/host helpers for libb200st (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace b200st {
+
+enum DType : int { F32 = 0, BF16 = 1 };
+
+// ---- error plumbing (thread-local last error string, C-ABI returns int) -----------------
+void set_last_error(const std::string& s);
+#define B200ST_FAIL(msg)                                                                   \
+  do {                                                                                     \
+    ::b200st::set_last_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+    return 1;                                                                              \
+  } while (0)
+#define B200ST_CHECK(cond, msg)                                                            \
+  do {                                                                                     \
+    if (!(cond)) B200ST_FAIL(std::string("check failed: " #cond " — ") + (msg));          \
+  } while (0)
+#define B200ST_CUDA(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) B200ST_FAIL(std::string(#expr ": ") + cudaGetErrorString(_e));  \
+  } while (0)
+#define B200ST_TRY(expr)                                                                   \
+  do {                                                                                     \
+    int _r = (expr);                                                                       \
+    if (_r != 0) return _r;                                                                \
+  } while (0)
+#define B200ST_LAUNCH_CHECK() B200ST_CUDA(cudaGetLastError())
+
+// ---- dtype helpers -----------------------------------------------------------------------
+template <typename T> struct DTypeOf;
+template <> struct DTypeOf<float> { static constexpr int value = F32; };
+template <> struct DTypeOf<__nv_bfloat16> { static constexpr int value = BF16; };
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_as_f32(const void* p, int dtype, int64_t idx) {
+  return dtype == F32 ? reinterpret_cast<const float*>(p)[idx]
+                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+}
+__device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t idx, float v) {
+  if (dtype == F32) reinterpret_cast<float*>(p)[idx] = v;
+  else reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
+}
+
+// ---- warp / block reductions ------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- counter-based RNG for dropout: Philox4x32-10 --------------------------------------
+// One call yields 4 x 32 random bits for counter (idx4, stream) under key (seed).  Dropout at element
+// index e uses call (e >> 2) and lane (e & 3), so forward and backward regenerate identical masks.
+struct Philox4 { uint32_t x, y, z, w; };
+__host__ __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t counter, uint64_t stream) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32);
+  uint32_t c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    uint32_t lo0 = mulhilo32(0xD2511F53u, c0, &hi0);
+    uint32_t lo1 = mulhilo32(0xCD9E8D57u, c2, &hi1);
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+// keep-decision for element `e` of dropout site `stream`; keep iff u >= p  (u uniform in [0,1))
+__host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t stream, uint64_t e, float p) {
+  Philox4 r = philox4x32_10(seed, e >> 2, stream);
+  uint32_t bits = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+  float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
+  return u >= p;
+}
+
+struct DropoutSpec {
+  float p;          // 0 => disabled
+  float scale;      // 1/(1-p)
+  uint64_t seed;
+  uint64_t stream;  // unique id of the dropout site (layer, op)
+};
+__host__ __device__ __forceinline__ DropoutSpec no_dropout() { return DropoutSpec{0.f, 1.f, 0, 0}; }
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace b200st

@@ -1,0 +1,445 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for sm_100a.
+//
+// Persistent, warp-specialised kernel (one CTA per SM, 192 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, 2 stages)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Tile: 128 x BN x 64 (BN in {64,128,256}); operands may be K-major or MN-major (wgrad / PV products),
+// batched through 4-D tensor maps; optional split-K with fp32 RED accumulation.
+//
+// Replaces the cuBLAS calls behind tf.einsum / Dense / Conv2D at the reference sites listed in
+// SURVEY.md §2.3 (K3,K4,K8,K9,K10,K11,K13,K15), e.g. neurst/layers/common_layers.py:270,276-288.
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <cstring>
+
+namespace b200st {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                  // 64 bf16 = 128 B = one swizzle row
+constexpr int kThreads = 192;
+constexpr int kSmemLimit = 232448;      // 227 KB
+constexpr uint32_t kABytes = BM * BK * 2;
+
+struct TcParams {
+  int M, N, K;
+  int nb1, nb2;
+  int m_tiles, n_tiles, splitk, kb_total, kb_per_split;
+  int64_t num_tiles;
+  int stages;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // descriptor byte offsets
+  uint32_t a_kstep, b_kstep;             // smem byte advance per UMMA_K=16
+  uint32_t idesc;
+  void* C;
+  int c_dtype;
+  int64_t ldc, c_sb1, c_sb2;
+  GemmEpilogue epi;
+  int atomic;
+};
+
+struct TileCoord { int b2, b1, m_blk, n_blk, split; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile) {
+  TileCoord t;
+  t.split = (int)(tile % p.splitk); tile /= p.splitk;
+  t.n_blk = (int)(tile % p.n_tiles); tile /= p.n_tiles;
+  t.m_blk = (int)(tile % p.m_tiles); tile /= p.m_tiles;
+  t.b1 = (int)(tile % p.nb1);
+  t.b2 = (int)(tile / p.nb1);
+  return t;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kBBytes = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * kStageBytes;   // 8-byte barriers
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int kb0 = t.split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          ptx::mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              ptx::tma_load_4d(sa + c * (64 * BK * 2), &tmA, full_bar(stage), t.m_blk * BM + c * 64, kb * BK, t.b1, t.b2);
+          } else {
+            ptx::tma_load_4d(sa, &tmA, full_bar(stage), kb * BK, t.m_blk * BM, t.b1, t.b2);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              ptx::tma_load_4d(sb + c * (64 * BK * 2), &tmB, full_bar(stage), t.n_blk * BN + c * 64, kb * BK, t.b1, t.b2);
+          } else {
+            ptx::tma_load_4d(sb, &tmB, full_bar(stage), kb * BK, t.n_blk * BN, t.b1, t.b2);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int kb0 = t.split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = ptx::make_smem_desc_sw128(sa + k * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t db = ptx::make_smem_desc_sw128(sb + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            ptx::mma_f16_ss(tmem_d, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(empty_bar(stage));     // frees the smem slot when these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tfull_bar(acc));         // accumulator ready for the epilogue warps
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const GemmEpilogue& ep = p.epi;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int kb0 = t.split * p.kb_per_split;
+      const bool has_work = kb0 < p.kb_total;     // a trailing split may be empty
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const int m = t.m_blk * BM + row_in_tile;
+      const int64_t bidx = (int64_t)t.b2 * p.nb1 + t.b1;
+      const int64_t boff_c = (int64_t)t.b2 * p.c_sb2 + (int64_t)t.b1 * p.c_sb1;
+      const int64_t boff_mask = (int64_t)t.b2 * ep.mask_sb2 + (int64_t)t.b1 * ep.mask_sb1;
+      const int64_t boff_res = (int64_t)t.b2 * ep.res_sb2 + (int64_t)t.b1 * ep.res_sb1;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = t.n_blk * BN + c0;
+        if (n0 >= p.N) break;                     // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr_row + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (m < p.M && has_work) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            const uint64_t e_idx = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n);
+            v[j] = (n < p.N) ? gemm_epilogue_value(ep, __uint_as_float(r[j]), m, n, boff_mask, boff_res, e_idx) : 0.f;
+          }
+          const int64_t row_off = boff_c + (int64_t)m * p.ldc + n0;
+          const bool full = (n0 + 32 <= p.N);
+          if (p.atomic) {
+            float* c = reinterpret_cast<float*>(p.C) + row_off;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) atomicAdd(c + j, v[j]);
+          } else if (p.c_dtype == F32) {
+            float* c = reinterpret_cast<float*>(p.C) + row_off;
+            if (ep.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) c[j] += v[j];
+            } else if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) c[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + row_off;
+            if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(c + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) c[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Host side: tensor-map construction (driver entry point fetched at run time; no libcuda link)
+// -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  uint64_t v[10];
+  bool operator==(const MapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// Operand tensor map: dims (inner, outer, nb1, nb2); inner = K (K-major) or M/N (MN-major).
+int make_operand_map(const GemmOperand& op, int rows, int K, int nb1, int nb2, int box_rows_kmajor, CUtensorMap* out) {
+  EncodeTiledFn fn = get_encode_fn();
+  B200ST_CHECK(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const uint64_t es = 2;
+  uint64_t inner = op.mn_major ? (uint64_t)rows : (uint64_t)K;
+  uint64_t outer = op.mn_major ? (uint64_t)K : (uint64_t)rows;
+  uint64_t sb1 = nb1 > 1 ? (uint64_t)op.sb1 : (uint64_t)op.ld * outer;
+  uint64_t sb2 = nb2 > 1 ? (uint64_t)op.sb2 : sb1 * (uint64_t)nb1;
+  if (sb1 == 0) sb1 = (uint64_t)op.ld * outer;   // broadcast batch strides are not used by callers of the TC path
+  if (sb2 == 0) sb2 = sb1 * (uint64_t)nb1;
+  cuuint64_t dims[4] = {inner, outer, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)op.ld * es, sb1 * es, sb2 * es};
+  cuuint32_t box[4] = {64u, (cuuint32_t)(op.mn_major ? BK : box_rows_kmajor), 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  B200ST_CHECK((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "TMA operand base must be 16-byte aligned");
+  B200ST_CHECK(strides[0] % 16 == 0 && strides[1] % 16 == 0 && strides[2] % 16 == 0,
+               "TMA operand strides must be multiples of 16 bytes (ld % 8 == 0 for bf16)");
+  MapKey key{{(uint64_t)(uintptr_t)op.ptr, inner, outer, (uint64_t)nb1, (uint64_t)nb2, strides[0], strides[1], strides[2],
+              box[1], (uint64_t)op.mn_major}};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return 0; }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) B200ST_FAIL("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_map_cache.size() > 65536) g_map_cache.clear();
+  g_map_cache.emplace(key, *out);
+  return 0;
+}
+
+int g_num_sms = 0;
+int64_t g_launches = 0;
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int grid, size_t smem,
+                   cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(ta, tb, p);
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int grid,
+              size_t smem, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, p, grid, smem, stream);
+  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, p, grid, smem, stream);
+  if (a_mn && !b_mn) return launch_variant<BN, true, false>(ta, tb, p, grid, smem, stream);
+  return launch_variant<BN, true, true>(ta, tb, p, grid, smem, stream);
+}
+
+}  // namespace
+
+TcDebug& tc_debug() {
+  static TcDebug d{};
+  return d;
+}
+int64_t tc_launch_count() { return g_launches; }
+
+int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
+  B200ST_CHECK(g.A.dtype == BF16 && g.B.dtype == BF16, "tcgen05 GEMM needs bf16 operands");
+  B200ST_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "empty GEMM");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B200ST_CUDA(cudaGetDevice(&dev));
+    B200ST_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const TcDebug& dbg = tc_debug();
+  const int num_sms = dbg.max_ctas > 0 ? dbg.max_ctas : g_num_sms;
+
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.nb1 = g.nb1; p.nb2 = g.nb2;
+  p.m_tiles = ceil_div(g.M, BM);
+  p.kb_total = ceil_div(g.K, BK);
+  const int64_t batch = (int64_t)g.nb1 * g.nb2;
+
+  // ---- split-K (only for linear fp32 accumulation epilogues) ----
+  int splitk = g.splitk;
+  const bool linear_epi = !g.epi.relu && !g.epi.mask_src && g.epi.drop.p == 0.f && !g.epi.residual && !g.epi.bias;
+  if (splitk == 0) {   // auto
+    splitk = 1;
+    if (linear_epi && g.c_dtype == F32 && g.epi.accumulate) {
+      const int64_t base_tiles = batch * p.m_tiles * ceil_div(g.N, 128);
+      while (base_tiles * splitk * 2 <= num_sms && p.kb_total / (splitk * 2) >= 4) splitk *= 2;
+      if (base_tiles * splitk < num_sms && p.kb_total / splitk >= 8) {
+        int want = (int)((num_sms + base_tiles - 1) / base_tiles);
+        int maxs = p.kb_total / 4;
+        splitk = want < maxs ? want : (maxs > 0 ? maxs : 1);
+      }
+    }
+  }
+  if (splitk > 1) {
+    B200ST_CHECK(linear_epi && g.c_dtype == F32, "split-K needs a linear fp32 epilogue");
+    if (splitk > p.kb_total) splitk = p.kb_total;
+  }
+  p.kb_per_split = ceil_div(p.kb_total, splitk);
+  splitk = ceil_div(p.kb_total, p.kb_per_split);   // no empty trailing split
+  p.splitk = splitk;
+  p.atomic = (splitk > 1) ? 1 : 0;
+
+  // ---- BN selection: fewest (waves x tile cost) ----
+  int bn = dbg.force_bn;
+  if (bn == 0) {
+    double best = 1e30;
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (c > 64 && c >= 2 * ((g.N + 63) / 64 * 64)) continue;   // do not pad N by 2x or more
+      int64_t tiles = batch * p.m_tiles * ceil_div(g.N, c) * splitk;
+      int64_t waves = (tiles + num_sms - 1) / num_sms;
+      double cost = (double)waves * ((double)c * p.kb_per_split + 96.0 + 0.5 * c);
+      if (cost < best) { best = cost; bn = c; }
+    }
+  }
+  p.n_tiles = ceil_div(g.N, bn);
+  p.num_tiles = batch * p.m_tiles * p.n_tiles * splitk;
+
+  const uint32_t stage_bytes = kABytes + (uint32_t)bn * BK * 2;
+  int stages = dbg.force_stages > 0 ? dbg.force_stages : (int)((kSmemLimit - 2048) / stage_bytes);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 5) + 16;
+  B200ST_CHECK(smem <= (size_t)kSmemLimit, "smem budget exceeded");
+
+  // descriptors
+  const uint32_t mn_lbo = dbg.mn_lbo_bytes ? dbg.mn_lbo_bytes : 64u * BK * 2;   // next 64-wide MN chunk (TMA box)
+  const uint32_t mn_sbo = dbg.mn_sbo_bytes ? dbg.mn_sbo_bytes : 1024u;          // next group of 8 k-rows
+  const uint32_t k_lbo = dbg.k_lbo_bytes ? dbg.k_lbo_bytes : 16u;               // ignored for swizzled K-major
+  const uint32_t k_sbo = dbg.k_sbo_bytes ? dbg.k_sbo_bytes : 1024u;             // next group of 8 rows
+  p.a_lbo = g.A.mn_major ? mn_lbo : k_lbo;  p.a_sbo = g.A.mn_major ? mn_sbo : k_sbo;
+  p.b_lbo = g.B.mn_major ? mn_lbo : k_lbo;  p.b_sbo = g.B.mn_major ? mn_sbo : k_sbo;
+  p.a_kstep = g.A.mn_major ? 16u * 128u : 32u;
+  p.b_kstep = g.B.mn_major ? 16u * 128u : 32u;
+  p.idesc = ptx::make_idesc_bf16(bn, g.A.mn_major, g.B.mn_major);
+
+  p.C = g.C; p.c_dtype = g.c_dtype; p.ldc = g.ldc; p.c_sb1 = g.c_sb1; p.c_sb2 = g.c_sb2;
+  p.epi = g.epi;
+  if (g.epi.accumulate) B200ST_CHECK(g.c_dtype == F32, "accumulate needs fp32 C");
+
+  CUtensorMap ta, tb;
+  B200ST_TRY(make_operand_map(g.A, g.M, g.K, g.nb1, g.nb2, BM, &ta));
+  B200ST_TRY(make_operand_map(g.B, g.N, g.K, g.nb1, g.nb2, bn, &tb));
+
+  const int grid = (int)(p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  ++g_launches;
+  switch (bn) {
+    case 64: return launch_bn<64>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream);
+    case 128: return launch_bn<128>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream);
+    case 256: return launch_bn<256>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream);
+    default: B200ST_FAIL("unsupported BN");
+  }
+}
+
+}  // namespace b200st

@@ -1,0 +1,127 @@
+"""ctypes binding of libb200st.so (the C-ABI boundary declared in include/b200st.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200st.so")
+_lib = None
+
+F32, BF16 = 0, 1
+
+
+class B200STError(RuntimeError):
+    pass
+
+
+class Operand(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("mn_major", C.c_int32),
+                ("ld", C.c_int64), ("sb1", C.c_int64), ("sb2", C.c_int64)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nb1", C.c_int32), ("nb2", C.c_int32),
+                ("A", Operand), ("B", Operand),
+                ("C", C.c_void_p), ("c_dtype", C.c_int32), ("ldc", C.c_int64), ("c_sb1", C.c_int64),
+                ("c_sb2", C.c_int64),
+                ("alpha", C.c_float), ("bias", C.c_void_p), ("relu", C.c_int32),
+                ("mask_src", C.c_void_p), ("mask_dtype", C.c_int32), ("mask_ld", C.c_int64),
+                ("mask_sb1", C.c_int64), ("mask_sb2", C.c_int64),
+                ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_stream", C.c_uint64),
+                ("residual", C.c_void_p), ("res_ld", C.c_int64), ("res_sb1", C.c_int64), ("res_sb2", C.c_int64),
+                ("accumulate", C.c_int32), ("splitk", C.c_int32), ("force_simt", C.c_int32)]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Loads libb200st.so, building it with nvcc when the in-tree binary is absent/stale and nvcc exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        try:
+            from neurst_b200.csrc import build as _build
+            _build.build()
+        except Exception as e:  # noqa
+            if not os.path.exists(_LIB_PATH):
+                raise B200STError("libb200st.so is missing and could not be built: %s" % e)
+    if not os.path.exists(_LIB_PATH):
+        raise B200STError("libb200st.so not found at %s (run `python -m neurst_b200.csrc.build`)" % _LIB_PATH)
+    lib = C.CDLL(_LIB_PATH)
+    lib.b200st_last_error.restype = C.c_char_p
+    lib.b200st_version.restype = C.c_int
+    lib.b200st_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B200STError(load().b200st_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().b200st_launch_count())
+
+
+def _dt(t):
+    import torch
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise B200STError("unsupported dtype %s" % t.dtype)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(A, B, Cout, a_mn=False, b_mn=False, alpha=1.0, bias=None, relu=False, mask_src=None, dropout=None,
+         residual=None, accumulate=False, splitk=1, force_simt=False):
+    """Generic contraction on 2-D/3-D/4-D torch CUDA tensors (tests & glue).
+
+    A: [..., M, K] (K-major) or [..., K, M] (a_mn); B: [..., N, K] or [..., K, N] (b_mn); Cout: [..., M, N].
+    Leading dims (0, 1 or 2 of them) are batch dims; inner dim must be contiguous.
+    """
+    lib = load()
+
+    def norm(t):
+        while t.dim() < 4:
+            t = t.unsqueeze(0)
+        assert t.stride(-1) == 1
+        return t
+
+    A4, B4, C4 = norm(A), norm(B), norm(Cout)
+    g = GemmArgs()
+    M, N = C4.shape[-2], C4.shape[-1]
+    K = A4.shape[-2] if a_mn else A4.shape[-1]
+    g.M, g.N, g.K = M, N, K
+    g.nb2, g.nb1 = C4.shape[0], C4.shape[1]
+    g.A = Operand(A4.data_ptr(), _dt(A4), int(a_mn), A4.stride(-2), A4.stride(1), A4.stride(0))
+    g.B = Operand(B4.data_ptr(), _dt(B4), int(b_mn), B4.stride(-2), B4.stride(1), B4.stride(0))
+    g.C, g.c_dtype, g.ldc, g.c_sb1, g.c_sb2 = C4.data_ptr(), _dt(C4), C4.stride(-2), C4.stride(1), C4.stride(0)
+    g.alpha = alpha
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.relu = int(relu)
+    if mask_src is not None:
+        m4 = norm(mask_src)
+        g.mask_src, g.mask_dtype = m4.data_ptr(), _dt(m4)
+        g.mask_ld, g.mask_sb1, g.mask_sb2 = m4.stride(-2), m4.stride(1), m4.stride(0)
+    if dropout is not None:
+        g.dropout_p, g.dropout_seed, g.dropout_stream = dropout
+    if residual is not None:
+        r4 = norm(residual)
+        g.residual = r4.data_ptr()
+        g.res_ld, g.res_sb1, g.res_sb2 = r4.stride(-2), r4.stride(1), r4.stride(0)
+    g.accumulate = int(accumulate)
+    g.splitk = splitk
+    g.force_simt = int(force_simt)
+    check(lib.b200st_gemm(C.byref(g), _stream()))
+    return Cout
