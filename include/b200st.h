@@ -49,6 +49,9 @@ typedef struct {
 } b200st_gemm_args;
 int b200st_gemm(const b200st_gemm_args* args, void* stream);
 
+/* tests/bench only: time `iters` back-to-back launches of one GEMM with CUDA events on `stream` (no host overhead) */
+int b200st_gemm_bench(const b200st_gemm_args* args, int32_t iters, float* ms_per_iter, void* stream);
+
 /* tests only: override tcgen05 shared-memory descriptor fields / tile config (0 = default) */
 int b200st_debug_tc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t k_lbo, uint32_t k_sbo, int32_t force_bn,
                     int32_t force_stages, int32_t max_ctas);

@@ -22,9 +22,39 @@ static GemmOperand to_operand(const b200st_operand& o) {
   return r;
 }
 
+static int convert_gemm(const b200st_gemm_args* a, GemmArgs& g);
+
 int b200st_gemm(const b200st_gemm_args* a, void* stream) {
   if (!a) B200ST_FAIL("null args");
-  GemmArgs g = gemm_defaults();
+  GemmArgs g;
+  B200ST_TRY(convert_gemm(a, g));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->force_simt) { if (g.splitk != 1) g.splitk = 1; return gemm_simt_f32(g, s); }
+  return gemm(g, s);
+}
+
+int b200st_gemm_bench(const b200st_gemm_args* a, int32_t iters, float* ms_per_iter, void* stream) {
+  if (!a || !ms_per_iter || iters <= 0) B200ST_FAIL("bad args");
+  GemmArgs g;
+  B200ST_TRY(convert_gemm(a, g));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  B200ST_CUDA(cudaEventCreate(&e0));
+  B200ST_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) B200ST_TRY(gemm(g, s));
+  B200ST_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i) B200ST_TRY(gemm(g, s));
+  B200ST_CUDA(cudaEventRecord(e1, s));
+  B200ST_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B200ST_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_iter = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+static int convert_gemm(const b200st_gemm_args* a, GemmArgs& g) {
+  g = gemm_defaults();
   g.M = a->M; g.N = a->N; g.K = a->K; g.nb1 = a->nb1 > 0 ? a->nb1 : 1; g.nb2 = a->nb2 > 0 ? a->nb2 : 1;
   g.A = to_operand(a->A); g.B = to_operand(a->B);
   g.C = a->C; g.c_dtype = a->c_dtype; g.ldc = a->ldc; g.c_sb1 = a->c_sb1; g.c_sb2 = a->c_sb2;
@@ -40,9 +70,7 @@ int b200st_gemm(const b200st_gemm_args* a, void* stream) {
   g.epi.residual = a->residual; g.epi.res_ld = a->res_ld; g.epi.res_sb1 = a->res_sb1; g.epi.res_sb2 = a->res_sb2;
   g.epi.accumulate = a->accumulate;
   g.splitk = a->splitk;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->force_simt) { if (g.splitk != 1) g.splitk = 1; return gemm_simt_f32(g, s); }
-  return gemm(g, s);
+  return 0;
 }
 
 int b200st_debug_tc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t k_lbo, uint32_t k_sbo, int32_t force_bn,

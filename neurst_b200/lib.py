@@ -83,14 +83,8 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def gemm(A, B, Cout, a_mn=False, b_mn=False, alpha=1.0, bias=None, relu=False, mask_src=None, dropout=None,
-         residual=None, accumulate=False, splitk=1, force_simt=False):
-    """Generic contraction on 2-D/3-D/4-D torch CUDA tensors (tests & glue).
-
-    A: [..., M, K] (K-major) or [..., K, M] (a_mn); B: [..., N, K] or [..., K, N] (b_mn); Cout: [..., M, N].
-    Leading dims (0, 1 or 2 of them) are batch dims; inner dim must be contiguous.
-    """
-    lib = load()
+def _gemm_args(A, B, Cout, a_mn=False, b_mn=False, alpha=1.0, bias=None, relu=False, mask_src=None, dropout=None,
+               residual=None, accumulate=False, splitk=1, force_simt=False):
 
     def norm(t):
         while t.dim() < 4:
@@ -123,5 +117,23 @@ def gemm(A, B, Cout, a_mn=False, b_mn=False, alpha=1.0, bias=None, relu=False, m
     g.accumulate = int(accumulate)
     g.splitk = splitk
     g.force_simt = int(force_simt)
-    check(lib.b200st_gemm(C.byref(g), _stream()))
+    return g
+
+
+def gemm(A, B, Cout, **kw):
+    """Generic contraction on 2-D/3-D/4-D torch CUDA tensors (tests & glue).
+
+    A: [..., M, K] (K-major) or [..., K, M] (a_mn); B: [..., N, K] or [..., K, N] (b_mn); Cout: [..., M, N].
+    Leading dims (0, 1 or 2 of them) are batch dims; inner dim must be contiguous.
+    """
+    g = _gemm_args(A, B, Cout, **kw)
+    check(load().b200st_gemm(C.byref(g), _stream()))
     return Cout
+
+
+def gemm_bench(A, B, Cout, iters=50, **kw):
+    """ms per launch of one GEMM, timed with CUDA events inside the library (no Python overhead)."""
+    g = _gemm_args(A, B, Cout, **kw)
+    ms = C.c_float(0)
+    check(load().b200st_gemm_bench(C.byref(g), iters, C.byref(ms), _stream()))
+    return ms.value
