@@ -49,6 +49,104 @@ typedef struct {
 } b200st_gemm_args;
 int b200st_gemm(const b200st_gemm_args* args, void* stream);
 
+
+/* ---- model handle ------------------------------------------------------------------------------------
+ * model_type: 0 = SpeechTransformer (neurst/models/speech_transformer.py:27-280), 1 = text Transformer
+ * (neurst/models/transformer.py), 2 = TransformerEncoder stack only (layers/encoders/transformer_encoder.py:23-136),
+ * 3 = TransformerDecoder stack only (layers/decoders/transformer_decoder.py:23-228), 4 = MultiHeadAttention /
+ * MultiHeadSelfAttention (layers/attentions/multi_head_attention.py:21-290).
+ * precision: B200ST_F32 = fp32 FMA kernels (parity mode, any shape); B200ST_BF16 = tcgen05 kernels. */
+typedef struct b200st_model* b200st_handle;
+typedef struct {
+  int32_t model_type;
+  int32_t d, heads, ffn, enc_layers, dec_layers, vocab, src_vocab;
+  int32_t feat, in_channels, channels, conv_layer_norm;
+  int32_t precision;
+  float ln_eps, attention_dropout, ffn_dropout, postprocess_dropout, label_smoothing;
+  int32_t share_src_trg_embedding;
+  int32_t mha_self, mha_din, mha_dmem, mha_dout;
+  int32_t with_cross_attention;
+} b200st_config;
+
+int b200st_create(const b200st_config* cfg, b200st_handle* out);   /* host object only; no device memory */
+int b200st_destroy(b200st_handle h);
+
+/* Parameter arena: one flat fp32 buffer; tensors in the reference's TF layouts (dense [in,out], conv HWIO,
+ * embedding [V,d]), each starting at a multiple of 8 elements. */
+int64_t b200st_param_arena_numel(b200st_handle h);
+int32_t b200st_param_count(b200st_handle h);
+int b200st_param_info(b200st_handle h, int32_t i, char* name, int32_t name_cap, int64_t* offset, int32_t* ndim,
+                      int64_t* shape4);
+
+typedef struct {
+  const float* params;      /* fp32 master arena */
+  const void* shadow;       /* bf16 copy of the arena (precision bf16 only; b200st_refresh_shadow / b200st_adam_step) */
+  float* grads;             /* fp32, same layout; gradients are ACCUMULATED into it */
+  void* workspace; uint64_t workspace_bytes;   /* >= b200st_workspace_bytes(...) , 256-byte aligned */
+} b200st_buffers;
+
+/* One batch in the reference's input-dict form (neurst/tasks/speech2text.py:135-161). */
+typedef struct {
+  const float* src;             /* speech: fp32 [B,T,feat,in_channels] */
+  const int64_t* src_ids;       /* text:   [B,T] */
+  const int64_t* src_length;    /* speech: [B] frames */
+  const float* src_padding;     /* text:   [B,T] 1.0 = pad */
+  const int64_t* trg_input;     /* [B,L] */
+  const int64_t* trg;           /* [B,L] or NULL */
+  const int64_t* trg_length;    /* [B]   or NULL */
+  int32_t B, T, L;
+  int32_t training;             /* dropout on */
+  uint64_t seed;                /* dropout seed of this step */
+  float loss_scale;             /* multiplies the loss gradient (0 => 1) */
+  float* logits;                /* out, optional: fp32 [B,L,V] */
+  float* loss;                  /* out, optional: [1] = sum(nll)/sum(tokens) (label_smoothed_cross_entropy.py:46-53) */
+  float* nll_sum;               /* out, optional: [B] */
+  float* n_tokens;              /* out, optional: [B] */
+  float* enc_out;               /* out, optional: fp32 [B,T',d] */
+} b200st_batch;
+
+int64_t b200st_workspace_bytes(b200st_handle h, int32_t B, int32_t T, int32_t L, int32_t training);
+/* EncoderDecoderModel.call (+ criterion when trg given): neurst/models/encoder_decoder_model.py:263-279 */
+int b200st_forward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream);
+/* forward + label-smoothed CE + full backward (GradAccumKerasModel.train_step, gradaccum_keras_model.py:190-245) */
+int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream);
+
+/* bf16 shadow of the parameter arena (tcgen05 operands) */
+int b200st_refresh_shadow(const float* params, void* shadow, int64_t numel, void* stream);
+/* Keras Adam, epsilon-hat form (neurst/optimizers/__init__.py:21; hparams speech_transformer.py:265-270):
+ * g' = g*grad_scale; m,v update; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps); optional bf16 shadow refresh + g=0 */
+int b200st_adam_step(float* params, float* grads, float* m, float* v, void* shadow, int64_t numel, float lr, float beta1,
+                     float beta2, float eps, int64_t step_t, float grad_scale, int32_t zero_grad, void* stream);
+
+/* layer-level forward (reference layer API).  need_bytes != NULL: only report the workspace size. */
+int b200st_encoder_forward(b200st_handle h, const b200st_buffers* buf, const float* x, const float* padding, int32_t B,
+                           int32_t T, float* out, int32_t training, uint64_t seed, void* stream, uint64_t* need_bytes);
+int b200st_decoder_forward(b200st_handle h, const b200st_buffers* buf, const float* x, const float* memory,
+                           const float* memory_padding, int32_t B, int32_t L, int32_t Tm, float* out, int32_t training,
+                           uint64_t seed, void* stream, uint64_t* need_bytes);
+int b200st_mha_forward(b200st_handle h, const b200st_buffers* buf, const float* query, const float* memory,
+                       const float* bias_2d, int32_t B, int32_t Tq, int32_t Tk, float* out, void* stream,
+                       uint64_t* need_bytes);
+
+/* criterion alone: LabelSmoothedCrossEntropy.__call__/reduce_loss (label_smoothed_cross_entropy.py:94-157,46-53) */
+int b200st_lsce(const float* logits, const int64_t* trg, const int64_t* trg_length, int32_t B, int32_t L, int32_t V,
+                float label_smoothing, float* nll_sum, float* n_tokens, float* loss, void* dlogits, int32_t dlogits_dtype,
+                float loss_scale, void* stream);
+/* LayerNormalization (common_layers.py:64-65) */
+int b200st_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps, void* y,
+                         int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t cols, int32_t relu, void* stream);
+int b200st_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                         const float* rstd, const float* gamma, const float* beta, const float* dres, void* dx,
+                         int32_t dx_dtype, float* dgamma, float* dbeta, int64_t rows, int32_t cols, int32_t relu, void* stream);
+/* conv subsampling front-end pieces (audio_modalities.py:84-109) */
+int b200st_conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta,
+                             void* y1, int32_t dtype, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t C,
+                             int32_t use_ln, void* stream);
+
+/* dropout bookkeeping for tests: the keep-mask (uint8) of site `stream_id` under `seed`, element i in [0,n) */
+uint64_t b200st_dropout_stream_id(const char* site);
+int b200st_dropout_mask(uint64_t seed, uint64_t stream_id, int64_t n, float p, uint8_t* out, void* stream);
+
 /* tests/bench only: time `iters` back-to-back launches of one GEMM with CUDA events on `stream` (no host overhead) */
 int b200st_gemm_bench(const b200st_gemm_args* args, int32_t iters, float* ms_per_iter, void* stream);
 

@@ -1,6 +1,10 @@
 // extern "C" surface of libb200st (see include/b200st.h).
 #include "../../include/b200st.h"
 #include "gemm.cuh"
+#include "kernels.cuh"
+#include "model.cuh"
+#include <cstring>
+#include <cmath>
 
 namespace b200st {
 static thread_local std::string g_last_error;
@@ -81,4 +85,157 @@ int b200st_debug_tc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t k_lbo, uint32_t k
   return 0;
 }
 
+
+struct b200st_model { Model m; };
+
+int b200st_create(const b200st_config* cfg, b200st_handle* out) {
+  if (!cfg || !out) B200ST_FAIL("null argument");
+  b200st_model* h = new b200st_model();
+  Config& c = h->m.cfg;
+  c.model_type = cfg->model_type;
+  c.d = cfg->d; c.heads = cfg->heads; c.ffn = cfg->ffn; c.enc_layers = cfg->enc_layers; c.dec_layers = cfg->dec_layers;
+  c.vocab = cfg->vocab; c.src_vocab = cfg->src_vocab;
+  c.feat = cfg->feat; c.in_channels = cfg->in_channels; c.channels = cfg->channels; c.conv_layer_norm = cfg->conv_layer_norm;
+  c.precision = cfg->precision;
+  c.ln_eps = cfg->ln_eps > 0.f ? cfg->ln_eps : 1e-6f;
+  c.attention_dropout = cfg->attention_dropout; c.ffn_dropout = cfg->ffn_dropout; c.postprocess_dropout = cfg->postprocess_dropout;
+  c.label_smoothing = cfg->label_smoothing;
+  c.share_src_trg_embedding = cfg->share_src_trg_embedding;
+  c.mha_self = cfg->mha_self; c.mha_din = cfg->mha_din; c.mha_dmem = cfg->mha_dmem; c.mha_dout = cfg->mha_dout;
+  c.with_cross_attention = cfg->with_cross_attention;
+  if (c.model_type < 0 || c.model_type > MODEL_MHA) { delete h; B200ST_FAIL("unknown model_type"); }
+  if (c.attention_dropout < 0 || c.attention_dropout >= 1 || c.ffn_dropout < 0 || c.ffn_dropout >= 1 ||
+      c.postprocess_dropout < 0 || c.postprocess_dropout >= 1) { delete h; B200ST_FAIL("dropout rates must be in [0,1)"); }
+  if (int r = build_param_table(h->m)) { delete h; return r; }
+  *out = h;
+  return 0;
+}
+int b200st_destroy(b200st_handle h) { delete h; return 0; }
+int64_t b200st_param_arena_numel(b200st_handle h) { return h ? h->m.arena_numel : -1; }
+int32_t b200st_param_count(b200st_handle h) { return h ? (int32_t)h->m.params.size() : -1; }
+int b200st_param_info(b200st_handle h, int32_t i, char* name, int32_t name_cap, int64_t* offset, int32_t* ndim, int64_t* shape4) {
+  if (!h || i < 0 || i >= (int)h->m.params.size()) B200ST_FAIL("bad parameter index");
+  const ParamInfo& p = h->m.params[i];
+  if (name && name_cap > 0) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (offset) *offset = p.offset;
+  if (ndim) *ndim = p.ndim;
+  if (shape4) for (int k = 0; k < 4; ++k) shape4[k] = p.shape[k];
+  return 0;
+}
+
+static Buffers to_buffers(const b200st_buffers* b) {
+  Buffers r{};
+  if (b) {
+    r.params = b->params; r.shadow = reinterpret_cast<const __nv_bfloat16*>(b->shadow); r.grads = b->grads;
+    r.workspace = b->workspace; r.workspace_bytes = (size_t)b->workspace_bytes;
+  }
+  return r;
+}
+static Batch to_batch(const b200st_batch* b) {
+  Batch r{};
+  r.src = b->src; r.src_ids = b->src_ids; r.src_length = b->src_length; r.src_padding = b->src_padding;
+  r.trg_input = b->trg_input; r.trg = b->trg; r.trg_length = b->trg_length;
+  r.B = b->B; r.T = b->T; r.L = b->L; r.training = b->training; r.seed = b->seed; r.loss_scale = b->loss_scale;
+  r.logits = b->logits; r.loss = b->loss; r.nll_sum = b->nll_sum; r.n_tokens = b->n_tokens; r.enc_out = b->enc_out;
+  return r;
+}
+
+int64_t b200st_workspace_bytes(b200st_handle h, int32_t B, int32_t T, int32_t L, int32_t training) {
+  if (!h) return -1;
+  return (int64_t)model_workspace_bytes(h->m, B, T, L, training);
+}
+int b200st_forward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream) {
+  if (!h || !buf || !batch) B200ST_FAIL("null argument");
+  if (batch->B <= 0 || batch->T <= 0 || batch->L <= 0) B200ST_FAIL("empty batch");
+  return model_forward(h->m, to_buffers(buf), to_batch(batch), false, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream) {
+  if (!h || !buf || !batch) B200ST_FAIL("null argument");
+  if (batch->B <= 0 || batch->T <= 0 || batch->L <= 0) B200ST_FAIL("empty batch");
+  return model_forward(h->m, to_buffers(buf), to_batch(batch), true, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_refresh_shadow(const float* params, void* shadow, int64_t numel, void* stream) {
+  if (!params || !shadow) B200ST_FAIL("null argument");
+  return cast_f32_to_bf16(params, reinterpret_cast<__nv_bfloat16*>(shadow), numel, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_adam_step(float* params, float* grads, float* m, float* v, void* shadow, int64_t numel, float lr, float beta1,
+                     float beta2, float eps, int64_t step_t, float grad_scale, int32_t zero_grad, void* stream) {
+  if (!params || !grads || !m || !v || step_t < 1) B200ST_FAIL("bad adam arguments");
+  const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step_t)) /
+                      (1.0 - std::pow((double)beta1, (double)step_t));
+  return adam_step(params, grads, m, v, reinterpret_cast<__nv_bfloat16*>(shadow), numel, (float)lr_t, beta1, beta2, eps,
+                   grad_scale, zero_grad, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_encoder_forward(b200st_handle h, const b200st_buffers* buf, const float* x, const float* padding, int32_t B,
+                           int32_t T, float* out, int32_t training, uint64_t seed, void* stream, uint64_t* need_bytes) {
+  if (!h) B200ST_FAIL("null handle");
+  size_t need = 0;
+  int r = encoder_forward_api(h->m, to_buffers(buf), x, padding, B, T, out, training, seed, reinterpret_cast<cudaStream_t>(stream),
+                              need_bytes ? &need : nullptr);
+  if (need_bytes) *need_bytes = need;
+  return r;
+}
+int b200st_decoder_forward(b200st_handle h, const b200st_buffers* buf, const float* x, const float* memory,
+                           const float* memory_padding, int32_t B, int32_t L, int32_t Tm, float* out, int32_t training,
+                           uint64_t seed, void* stream, uint64_t* need_bytes) {
+  if (!h) B200ST_FAIL("null handle");
+  size_t need = 0;
+  int r = decoder_forward_api(h->m, to_buffers(buf), x, memory, memory_padding, B, L, Tm, out, training, seed,
+                              reinterpret_cast<cudaStream_t>(stream), need_bytes ? &need : nullptr);
+  if (need_bytes) *need_bytes = need;
+  return r;
+}
+int b200st_mha_forward(b200st_handle h, const b200st_buffers* buf, const float* query, const float* memory,
+                       const float* bias_2d, int32_t B, int32_t Tq, int32_t Tk, float* out, void* stream, uint64_t* need_bytes) {
+  if (!h) B200ST_FAIL("null handle");
+  size_t need = 0;
+  int r = mha_forward_api(h->m, to_buffers(buf), query, memory, bias_2d, B, Tq, Tk, out, reinterpret_cast<cudaStream_t>(stream),
+                          need_bytes ? &need : nullptr);
+  if (need_bytes) *need_bytes = need;
+  return r;
+}
+int b200st_lsce(const float* logits, const int64_t* trg, const int64_t* trg_length, int32_t B, int32_t L, int32_t V,
+                float label_smoothing, float* nll_sum, float* n_tokens, float* loss, void* dlogits, int32_t dlogits_dtype,
+                float loss_scale, void* stream) {
+  if (!logits || !trg || !trg_length || !nll_sum || !n_tokens || !loss) B200ST_FAIL("null argument");
+  return lsce_fwd_bwd(logits, trg, trg_length, B, L, V, label_smoothing, nll_sum, n_tokens, loss, dlogits, dlogits_dtype,
+                      loss_scale > 0.f ? loss_scale : 1.f, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps, void* y,
+                         int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t cols, int32_t relu, void* stream) {
+  return layernorm_fwd(x, x_dtype, gamma, beta, eps, y, y_dtype, nullptr, mean, rstd, rows, cols, relu,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                         const float* rstd, const float* gamma, const float* beta, const float* dres, void* dx,
+                         int32_t dx_dtype, float* dgamma, float* dbeta, int64_t rows, int32_t cols, int32_t relu, void* stream) {
+  return layernorm_bwd(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, beta, dres, dx, dx_dtype, dgamma, dbeta, rows, cols, relu,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta,
+                             void* y1, int32_t dtype, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t C,
+                             int32_t use_ln, void* stream) {
+  return conv1_ln_relu_fwd(src, w, b, gamma, beta, 1e-6f, y1, dtype, B, T, F, Cin, C, use_ln, reinterpret_cast<cudaStream_t>(stream));
+}
+
+uint64_t b200st_dropout_stream_id(const char* site) { return site ? dropout_stream_id(site) : 0; }
+
 }  // extern "C"
+
+namespace b200st {
+__global__ void dropout_mask_kernel(uint64_t seed, uint64_t stream_id, int64_t n, float p, uint8_t* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = dropout_keep(seed, stream_id, (uint64_t)i, p) ? 1 : 0;
+}
+}  // namespace b200st
+
+extern "C" int b200st_dropout_mask(uint64_t seed, uint64_t stream_id, int64_t n, float p, uint8_t* out, void* stream) {
+  if (!out || n < 0) B200ST_FAIL("bad arguments");
+  if (n == 0) return 0;
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  b200st::dropout_mask_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(seed, stream_id, n, p, out);
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+

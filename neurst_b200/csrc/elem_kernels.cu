@@ -1,0 +1,540 @@
+// LayerNorm / softmax / dropout-cast / reductions / positions / embedding / label-smoothed CE / Adam.
+// HBM-bound kernels: coalesced accesses along the feature axis, warp-shuffle reductions, fp32 math.
+#include "kernels.cuh"
+#include <math.h>
+
+namespace b200st {
+
+#define DISPATCH_DTYPE(dt, T, ...)                                   \
+  do {                                                               \
+    if ((dt) == F32) { using T = float; __VA_ARGS__; }               \
+    else if ((dt) == BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else B200ST_FAIL("bad dtype");                                   \
+  } while (0)
+
+static inline int grid_for(int64_t work, int per_block, int cap = 148 * 16) {
+  int64_t g = (work + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  return (int)(g > cap ? cap : g);
+}
+
+// =============================================================================================
+// LayerNorm forward: one warp per row, values cached in registers for cols <= 1024
+// =============================================================================================
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, TY* __restrict__ y,
+                                                      float* __restrict__ y32, float* __restrict__ mean_out,
+                                                      float* __restrict__ rstd_out, int64_t rows, int cols, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const TX* xr = x + row * cols;
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) sum += to_f32(xr[c]);
+    const float mean = warp_sum(sum) / cols;
+    float sq = 0.f;
+    for (int c = lane; c < cols; c += 32) { float dlt = to_f32(xr[c]) - mean; sq += dlt * dlt; }
+    const float var = warp_sum(sq) / cols;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    for (int c = lane; c < cols; c += 32) {
+      float v = (to_f32(xr[c]) - mean) * rstd;
+      v = v * gamma[c] + beta[c];
+      if (relu) v = fmaxf(v, 0.f);
+      y[row * cols + c] = from_f32<TY>(v);
+      if (y32) y32[row * cols + c] = v;
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                  float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, cudaStream_t s) {
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows, 8);
+  DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,
+      (ln_fwd_kernel<TX, TY><<<grid, 256, 0, s>>>((const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// LayerNorm backward: warp per row for dx; per-lane column partials for dgamma/dbeta, block-reduced
+// =============================================================================================
+constexpr int LN_MAX_COLS_PER_LANE = 32;   // cols <= 1024
+
+template <typename TDY, typename TX, typename TDX>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ dres, TDX* __restrict__ dx,
+                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
+                                                      int cols, int relu) {
+  extern __shared__ float sm[];   // [2][cols] block partials
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float dg_acc[LN_MAX_COLS_PER_LANE], db_acc[LN_MAX_COLS_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) { dg_acc[i] = 0.f; db_acc[i] = 0.f; }
+  const int64_t warps_total = (int64_t)gridDim.x * nwarps;
+  for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += warps_total) {
+    const float mu = mean[row], rs = rstd[row];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) {
+        const float xh = (to_f32(x[row * cols + c]) - mu) * rs;
+        float d = to_f32(dy[row * cols + c]);
+        if (relu && (xh * gamma[c] + beta[c]) <= 0.f) d = 0.f;
+        const float g = d * gamma[c];
+        c1 += g; c2 += g * xh;
+        dg_acc[i] += d * xh; db_acc[i] += d;
+      }
+    }
+    c1 = warp_sum(c1) / cols; c2 = warp_sum(c2) / cols;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) {
+        const float xh = (to_f32(x[row * cols + c]) - mu) * rs;
+        float d = to_f32(dy[row * cols + c]);
+        if (relu && (xh * gamma[c] + beta[c]) <= 0.f) d = 0.f;
+        float v = rs * (d * gamma[c] - c1 - xh * c2);
+        if (dres) v += dres[row * cols + c];
+        dx[row * cols + c] = from_f32<TDX>(v);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) {
+    const int c = lane + 32 * i;
+    if (c < cols) { atomicAdd(&sm[c], dg_acc[i]); atomicAdd(&sm[cols + c], db_acc[i]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[c], sm[c]);
+    if (dbeta) atomicAdd(&dbeta[c], sm[cols + c]);
+  }
+}
+
+int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
+                  float* dbeta, int64_t rows, int cols, int relu, cudaStream_t s) {
+  if (rows == 0) return 0;
+  B200ST_CHECK(cols <= 32 * LN_MAX_COLS_PER_LANE, "layernorm_bwd supports cols <= 1024");
+  const int grid = grid_for(rows, 8 * 16, 148 * 4);
+  const size_t smem = 2 * (size_t)cols * sizeof(float);
+  DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,
+      (ln_bwd_kernel<TDY, TX, TDX><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres,
+                                                           (TDX*)dx, dgamma, dbeta, rows, cols, relu)))));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// softmax (+ additive key bias, causal mask, dropout) : one warp per (b,h,q) row
+// =============================================================================================
+constexpr float kFloatMin = -1.0e9f;   // neurst/utils/compat.py:24
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, int64_t ldS,
+                                                           const float* __restrict__ bias, int causal,
+                                                           T* __restrict__ P_pre, T* __restrict__ P_drop, int64_t ldP,
+                                                           int B, int H, int Tq, int Tk, DropoutSpec drop) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * H * Tq;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const int q = (int)(row % Tq);
+    const int b = (int)(row / ((int64_t)H * Tq));
+    const float* sr = S + row * ldS;
+    const float* br = bias ? bias + (int64_t)b * Tk : nullptr;
+    const int kmax_visible = q + (Tk - Tq);
+    float mx = -INFINITY;
+    for (int k = lane; k < Tk; k += 32) {
+      float v = sr[k];
+      if (br) v += br[k];
+      if (causal && k > kmax_visible) v += kFloatMin;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < Tk; k += 32) {
+      float v = sr[k];
+      if (br) v += br[k];
+      if (causal && k > kmax_visible) v += kFloatMin;
+      sum += expf(v - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int k = lane; k < Tk; k += 32) {
+      float v = sr[k];
+      if (br) v += br[k];
+      if (causal && k > kmax_visible) v += kFloatMin;
+      const float p = expf(v - mx) * inv;
+      P_pre[row * ldP + k] = from_f32<T>(p);
+      if (drop.p > 0.f) {
+        // dropout acts on the stored (rounded) probability so that backward sees identical values
+        const float ps = to_f32(from_f32<T>(p));
+        const bool keep = dropout_keep(drop.seed, drop.stream, (uint64_t)(row * Tk + k), drop.p);
+        P_drop[row * ldP + k] = from_f32<T>(keep ? ps * drop.scale : 0.f);
+      }
+    }
+  }
+}
+
+int softmax_fwd(const float* S, int64_t ldS, const float* bias, int causal, void* P_pre, void* P_drop, int p_dtype,
+                int64_t ldP, int B, int H, int Tq, int Tk, DropoutSpec drop, cudaStream_t s) {
+  const int64_t rows = (int64_t)B * H * Tq;
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows, 8);
+  DISPATCH_DTYPE(p_dtype, T, (softmax_fwd_kernel<T><<<grid, 256, 0, s>>>(S, ldS, bias, causal, (T*)P_pre, (T*)P_drop, ldP,
+                                                                          B, H, Tq, Tk, drop)));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ dP, int64_t ldS,
+                                                           const T* __restrict__ P_pre, T* __restrict__ dS, int64_t ldP,
+                                                           int64_t rows, int Tk, DropoutSpec drop) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    float dot = 0.f;
+    for (int k = lane; k < Tk; k += 32) {
+      float d = dP[row * ldS + k];
+      if (drop.p > 0.f) d = dropout_keep(drop.seed, drop.stream, (uint64_t)(row * Tk + k), drop.p) ? d * drop.scale : 0.f;
+      dot += d * to_f32(P_pre[row * ldP + k]);
+    }
+    dot = warp_sum(dot);
+    for (int k = lane; k < Tk; k += 32) {
+      float d = dP[row * ldS + k];
+      if (drop.p > 0.f) d = dropout_keep(drop.seed, drop.stream, (uint64_t)(row * Tk + k), drop.p) ? d * drop.scale : 0.f;
+      dS[row * ldP + k] = from_f32<T>(to_f32(P_pre[row * ldP + k]) * (d - dot));
+    }
+  }
+}
+
+int softmax_bwd(const float* dP, int64_t ldS, const void* P_pre, void* dS, int p_dtype, int64_t ldP, int64_t rows,
+                int Tk, DropoutSpec drop, cudaStream_t s) {
+  if (rows == 0) return 0;
+  const int grid = grid_for(rows, 8);
+  DISPATCH_DTYPE(p_dtype, T, (softmax_bwd_kernel<T><<<grid, 256, 0, s>>>(dP, ldS, (const T*)P_pre, (T*)dS, ldP, rows, Tk, drop)));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// elementwise: cast + dropout, posenc, fill, param cast
+// =============================================================================================
+template <typename T>
+__global__ void cast_dropout_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n, DropoutSpec drop) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (drop.p > 0.f) v = dropout_keep(drop.seed, drop.stream, (uint64_t)i, drop.p) ? v * drop.scale : 0.f;
+    y[i] = from_f32<T>(v);
+  }
+}
+int cast_dropout(const float* x, void* y, int y_dtype, int64_t n, DropoutSpec drop, cudaStream_t s) {
+  if (n == 0) return 0;
+  DISPATCH_DTYPE(y_dtype, T, (cast_dropout_kernel<T><<<grid_for(n, 256 * 4), 256, 0, s>>>(x, (T*)y, n, drop)));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ dY, int64_t M, int N, int64_t ld, float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (n < N)
+    for (int64_t m = (int64_t)blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8) acc += to_f32(dY[m * ld + n]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(&db[n], t);
+  }
+}
+int colsum_accum(const void* dY, int dtype, int64_t M, int N, int64_t ld, float* db, cudaStream_t s) {
+  if (M == 0 || N == 0) return 0;
+  dim3 block(32, 8);
+  int gy = (int)((M + 255) / 256);
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  dim3 grid(ceil_div(N, 32), gy);
+  DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, 0, s>>>((const T*)dY, M, N, ld, db)));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// sinusoid(t, c): [sin(t*w_i) | cos(t*w_i)], w_i = exp(-i * ln(1e4)/(d/2-1))  (common_layers.py:400-408)
+__device__ __forceinline__ float sinusoid(int t, int c, int d) {
+  const int half = d / 2;
+  if (c >= 2 * half) return 0.f;   // odd d: zero pad
+  const int i = c < half ? c : c - half;
+  const double inc = log(1.0e4) / ((double)half - 1.0);
+  const double arg = (double)t * exp(-(double)i * inc);
+  return (float)(c < half ? sin(arg) : cos(arg));
+}
+
+__global__ void posenc_fwd_kernel(const float* __restrict__ v, float* __restrict__ x, int B, int T, int d, float scale,
+                                  int t0, DropoutSpec drop) {
+  const int64_t n = (int64_t)B * T * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int t = (int)((i / d) % T);
+    float val = v[i] * scale + sinusoid(t + t0, c, d);
+    if (drop.p > 0.f) val = dropout_keep(drop.seed, drop.stream, (uint64_t)i, drop.p) ? val * drop.scale : 0.f;
+    x[i] = val;
+  }
+}
+int posenc_fwd(const float* v, float* x, int B, int T, int d, float scale, int t0, DropoutSpec drop, cudaStream_t s) {
+  const int64_t n = (int64_t)B * T * d;
+  if (n == 0) return 0;
+  posenc_fwd_kernel<<<grid_for(n, 256 * 2), 256, 0, s>>>(v, x, B, T, d, scale, t0, drop);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+__global__ void posenc_bwd_kernel(const float* __restrict__ dx, T* __restrict__ dv, int64_t n, float scale, DropoutSpec drop) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = dx[i];
+    if (drop.p > 0.f) g = dropout_keep(drop.seed, drop.stream, (uint64_t)i, drop.p) ? g * drop.scale : 0.f;
+    dv[i] = from_f32<T>(g * scale);
+  }
+}
+int posenc_bwd(const float* dx, void* dv, int dv_dtype, int64_t n, float scale, DropoutSpec drop, cudaStream_t s) {
+  if (n == 0) return 0;
+  DISPATCH_DTYPE(dv_dtype, T, (posenc_bwd_kernel<T><<<grid_for(n, 256 * 4), 256, 0, s>>>(dx, (T*)dv, n, scale, drop)));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E, float* __restrict__ x, int B,
+                                 int L, int d, int V, int t0, float scale, DropoutSpec drop) {
+  const int64_t n = (int64_t)B * L * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int64_t bl = i / d;
+    const int l = (int)(bl % L);
+    int64_t id = ids[bl];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    float val = E[id * d + c] * scale + sinusoid(l + t0, c, d);
+    if (drop.p > 0.f) val = dropout_keep(drop.seed, drop.stream, (uint64_t)i, drop.p) ? val * drop.scale : 0.f;
+    x[i] = val;
+  }
+}
+int embed_fwd(const int64_t* ids, const float* E, float* x, int B, int L, int d, int V, int t0, DropoutSpec drop,
+              cudaStream_t s) {
+  const int64_t n = (int64_t)B * L * d;
+  if (n == 0) return 0;
+  embed_fwd_kernel<<<grid_for(n, 256 * 2), 256, 0, s>>>(ids, E, x, B, L, d, V, t0, sqrtf((float)d), drop);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dE,
+                                 int B, int L, int d, int V, float scale, DropoutSpec drop) {
+  const int64_t n = (int64_t)B * L * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int64_t bl = i / d;
+    int64_t id = ids[bl];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    float g = dx[i];
+    if (drop.p > 0.f) g = dropout_keep(drop.seed, drop.stream, (uint64_t)i, drop.p) ? g * drop.scale : 0.f;
+    atomicAdd(&dE[id * d + c], g * scale);
+  }
+}
+int embed_bwd(const int64_t* ids, const float* dx, float* dE, int B, int L, int d, int V, DropoutSpec drop, cudaStream_t s) {
+  const int64_t n = (int64_t)B * L * d;
+  if (n == 0) return 0;
+  embed_bwd_kernel<<<grid_for(n, 256 * 2), 256, 0, s>>>(ids, dx, dE, B, L, d, V, sqrtf((float)d), drop);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void length_to_bias_kernel(const int64_t* __restrict__ lengths, float* __restrict__ bias, int B, int T, int n_halvings) {
+  const int64_t n = (int64_t)B * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T), t = (int)(i % T);
+    int64_t len = lengths[b];
+    for (int h = 0; h < n_halvings; ++h) len = (len + 1) / 2;
+    bias[i] = t >= len ? kFloatMin : 0.f;
+  }
+}
+int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s) {
+  if ((int64_t)B * T == 0) return 0;
+  length_to_bias_kernel<<<grid_for((int64_t)B * T, 256), 256, 0, s>>>(lengths, bias, B, T, n_halvings);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void padding_to_bias_kernel(const float* __restrict__ padding, float* __restrict__ bias, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bias[i] = padding[i] * kFloatMin;
+}
+int padding_to_bias(const float* padding, float* bias, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  padding_to_bias_kernel<<<grid_for(n, 256), 256, 0, s>>>(padding, bias, n);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// label-smoothed cross entropy: one block per (b,l) row of V logits
+// =============================================================================================
+__device__ __forceinline__ float block_reduce(float v, float* sm, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+  if (warp == 0) {
+    r = is_max ? warp_max(r) : warp_sum(r);
+    if (lane == 0) sm[0] = r;
+  }
+  __syncthreads();
+  return sm[0];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) lsce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ trg,
+                                                    const int64_t* __restrict__ trg_length, int B, int L, int V,
+                                                    float eps_ls, float* __restrict__ nll_sum, T* __restrict__ dlogits,
+                                                    float loss_scale) {
+  __shared__ float sm[32];
+  const int64_t row = blockIdx.x;
+  const int b = (int)(row / L), l = (int)(row % L);
+  const float w = (l < trg_length[b]) ? 1.f : 0.f;
+  // total token count (every block recomputes it: B is small)
+  float tok = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { int64_t len = trg_length[i]; tok += (float)(len < L ? (len < 0 ? 0 : len) : L); }
+  const float total_tokens = block_reduce(tok, sm, false);
+  const float* z = logits + row * V;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, z[v]);
+  mx = block_reduce(mx, sm, true);
+  float se = 0.f, sz = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) { se += expf(z[v] - mx); sz += z[v]; }
+  se = block_reduce(se, sm, false);
+  sz = block_reduce(sz, sm, false);
+  const float lse = mx + logf(se);
+  int64_t label = trg[row];
+  label = label < 0 ? 0 : (label >= V ? V - 1 : label);
+  const float conf = 1.f - eps_ls;
+  const float low = eps_ls / (float)(V - 1);
+  if (threadIdx.x == 0) {
+    const float lp_label = z[label] - lse;
+    const float sum_lp = sz - (float)V * lse;
+    float xent = -((conf - low) * lp_label + low * sum_lp);
+    if (eps_ls > 0.f) xent -= -(conf * logf(conf) + (float)(V - 1) * low * logf(low + 1e-20f));
+    atomicAdd(&nll_sum[b], xent * w);
+  }
+  if (dlogits) {
+    const float coef = (total_tokens > 0.f) ? w * loss_scale / total_tokens : 0.f;
+    T* dz = dlogits + row * V;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float p = expf(z[v] - lse);
+      dz[v] = from_f32<T>(coef * (p - (v == label ? conf : low)));
+    }
+  }
+}
+
+__global__ void lsce_finalize_kernel(const float* __restrict__ nll_sum, const int64_t* __restrict__ trg_length, int B, int L,
+                                     float* __restrict__ n_tokens, float* __restrict__ loss) {
+  __shared__ float sm[32];
+  float a = 0.f, t = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    int64_t len = trg_length[i];
+    const float tk = (float)(len < L ? (len < 0 ? 0 : len) : L);
+    n_tokens[i] = tk;
+    a += nll_sum[i]; t += tk;
+  }
+  a = block_reduce(a, sm, false);
+  t = block_reduce(t, sm, false);
+  if (threadIdx.x == 0) loss[0] = a / t;
+}
+
+int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_length, int B, int L, int V,
+                 float label_smoothing, float* nll_sum, float* n_tokens, float* loss, void* dlogits, int d_dtype,
+                 float loss_scale, cudaStream_t s) {
+  if (B * L == 0) return 0;
+  B200ST_CUDA(cudaMemsetAsync(nll_sum, 0, sizeof(float) * B, s));
+  DISPATCH_DTYPE(d_dtype, T, (lsce_kernel<T><<<B * L, 256, 0, s>>>(logits, trg, trg_length, B, L, V, label_smoothing, nll_sum,
+                                                                    (T*)dlogits, loss_scale)));
+  B200ST_LAUNCH_CHECK();
+  lsce_finalize_kernel<<<1, 256, 0, s>>>(nll_sum, trg_length, B, L, n_tokens, loss);
+  g_kernel_launches += 2;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// optimizer / parameter utilities
+// =============================================================================================
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, float b1, float b2, float eps,
+                            float gscale, int zero_grad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
+              float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s) {
+  if (n == 0) return 0;
+  adam_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  cast_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, y, n);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void fill_kernel(float* __restrict__ x, float v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+int fill_f32(float* x, float v, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  fill_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, v, n);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200st

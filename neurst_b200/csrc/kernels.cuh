@@ -1,0 +1,76 @@
+// Host launchers of the non-GEMM kernels (LayerNorm, softmax, dropout casts, reductions, positions,
+// embedding, label-smoothed CE, Adam, conv front-end).  All activations are `dtype`-tagged raw pointers
+// (F32 in the fp32 parity mode, BF16 in the tcgen05 mode); statistics, residual stream, gradients of
+// parameters and the loss are always fp32.
+#pragma once
+#include "common.cuh"
+
+namespace b200st {
+
+extern int64_t g_kernel_launches;
+
+// y = LN(x) (* gamma + beta) [relu]; x: [rows, cols] in x_dtype; y in y_dtype; optional fp32 copy y32.
+// mean / rstd (fp32 [rows]) may be null.  (neurst/layers/common_layers.py:64-65,77; audio_modalities.py:73-74,103-104)
+int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                  float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, cudaStream_t s);
+// dx = [dres +] LN'(dy) ; dgamma/dbeta += ; relu: dy is masked where LN(x)*gamma+beta <= 0 (conv front-end).
+int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
+                  float* dbeta, int64_t rows, int cols, int relu, cudaStream_t s);
+
+// P = softmax(S + bias[b, k] + causal) over k (multi_head_attention.py:147-160,207-208).
+// S fp32 [B,H,Tq,ldS]; bias fp32 [B,Tk] or null; causal: key k visible to query q iff k <= q + (Tk - Tq).
+// Writes P_pre and (if drop.p > 0) P_drop = dropout(P_pre), both `p_dtype` with row stride ldP.
+int softmax_fwd(const float* S, int64_t ldS, const float* bias, int causal, void* P_pre, void* P_drop, int p_dtype,
+                int64_t ldP, int B, int H, int Tq, int Tk, DropoutSpec drop, cudaStream_t s);
+// dS = P * (dP' - sum_k dP' P), dP' = dropout'(dP); dP fp32 [rows, ldS], output `p_dtype` [rows, ldP].
+int softmax_bwd(const float* dP, int64_t ldS, const void* P_pre, void* dS, int p_dtype, int64_t ldP, int64_t rows,
+                int Tk, DropoutSpec drop, cudaStream_t s);
+
+// y(dtype) = dropout(x fp32) over n elements (post-process dropout backward: common_layers.py:80-83)
+int cast_dropout(const float* x, void* y, int y_dtype, int64_t n, DropoutSpec drop, cudaStream_t s);
+// db[n] += sum_m dY[m, n]
+int colsum_accum(const void* dY, int dtype, int64_t M, int N, int64_t ld, float* db, cudaStream_t s);
+
+// x[b,t,:] = dropout(v[b,t,:] * scale + sinusoid(t + t0)) (common_layers.py:357-434); v fp32 -> x fp32
+int posenc_fwd(const float* v, float* x, int B, int T, int d, float scale, int t0, DropoutSpec drop, cudaStream_t s);
+// dv(dtype) = dropout'(dx) * scale
+int posenc_bwd(const float* dx, void* dv, int dv_dtype, int64_t n, float scale, DropoutSpec drop, cudaStream_t s);
+
+// x[b,l,:] = dropout(E[ids[b,l]] * sqrt(d) + sinusoid(l + t0)) (text_modalities.py:84-92)
+int embed_fwd(const int64_t* ids, const float* E, float* x, int B, int L, int d, int V, int t0, DropoutSpec drop,
+              cudaStream_t s);
+int embed_bwd(const int64_t* ids, const float* dx, float* dE, int B, int L, int d, int V, DropoutSpec drop,
+              cudaStream_t s);
+
+// bias[b,k] = (k >= len[b]) ? -1e9 : 0   with len from `lengths` after `n_conv` ceil-halvings
+// (speech_transformer.py:179-189, layer_utils.py:19-32)
+int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s);
+int padding_to_bias(const float* padding, float* bias, int64_t n, cudaStream_t s);
+
+// label-smoothed CE forward (+ backward when dlogits != null) (label_smoothed_cross_entropy.py:94-157,46-53)
+// logits fp32 [B*L, V]; outputs nll_sum[B], n_tokens[B], loss[1] = sum nll / sum tokens;
+// dlogits(dtype)[B*L, V] = w/sum_tokens * loss_scale * (softmax - soft_target)
+int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_length, int B, int L, int V,
+                 float label_smoothing, float* nll_sum, float* n_tokens, float* loss, void* dlogits, int d_dtype,
+                 float loss_scale, cudaStream_t s);
+
+// Keras Adam (epsilon-hat form) over a flat arena; optionally refreshes the bf16 shadow and zeroes g.
+int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
+              float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s);
+int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s);
+int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
+
+// ---- conv front-end (audio_modalities.py:84-109) ----
+// y1 = relu(LN(conv3x3s2(src) + b)); src fp32 [B,T,F,Cin]; w fp32 HWIO [3,3,Cin,C]; y1 (dtype) [B,T1,F1,C]
+int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
+                      void* y1, int y_dtype, int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s);
+int conv1_ln_relu_bwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
+                      const void* y1, const void* dy1, int dtype, float* dw, float* db, float* dgamma, float* dbeta,
+                      int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s);
+// col[(b,t2,f2), (kh,kw,c)] = y1[b, 2*t2+kh-1, 2*f2+kw-1, c] (zero outside)
+int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, cudaStream_t s);
+// dy1[b,t1,f1,c] = sum over taps of dcol (transpose of im2col)
+int col2im_3x3s2(const void* dcol, void* dy1, int dtype, int B, int T1, int F1, int C, cudaStream_t s);
+
+}  // namespace b200st

@@ -1,0 +1,94 @@
+// Model runtime of libb200st: configuration, parameter table (flat fp32 arena in the reference's TF layouts),
+// workspace planning and the forward / backward orchestration of the SpeechTransformer hot path.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace b200st {
+
+enum ModelType : int { MODEL_SPEECH = 0, MODEL_TEXT = 1, MODEL_ENCODER = 2, MODEL_DECODER = 3, MODEL_MHA = 4 };
+
+struct Config {
+  int model_type;
+  int d, heads, ffn, enc_layers, dec_layers, vocab, src_vocab;
+  int feat, in_channels, channels, conv_layer_norm;
+  int precision;              // F32: fp32 FMA kernels (parity mode); BF16: tcgen05 kernels
+  float ln_eps, attention_dropout, ffn_dropout, postprocess_dropout, label_smoothing;
+  int share_src_trg_embedding;
+  // MODEL_MHA only
+  int mha_self, mha_din, mha_dmem, mha_dout;
+  int with_cross_attention;   // decoder stack: 1 (default)
+};
+
+struct ParamInfo {
+  std::string name;
+  int64_t offset;   // elements in the arena (multiple of 8)
+  int ndim;
+  int64_t shape[4];
+  int64_t numel;
+};
+
+struct Model {
+  Config cfg;
+  std::vector<ParamInfo> params;
+  std::unordered_map<std::string, int> index;
+  int64_t arena_numel = 0;
+  int adt = F32;              // activation dtype
+  int find(const std::string& n) const {
+    auto it = index.find(n);
+    return it == index.end() ? -1 : it->second;
+  }
+};
+
+int build_param_table(Model& m);
+
+// Caller-provided device memory for one call.
+struct Buffers {
+  const float* params;                 // fp32 master arena
+  const __nv_bfloat16* shadow;         // bf16 copy of the arena (BF16 precision only)
+  float* grads;                        // fp32 gradient arena (accumulated into; null for inference)
+  void* workspace;
+  size_t workspace_bytes;
+};
+
+struct Batch {
+  // speech: src fp32 [B,T,feat,in_channels] + src_length[B]; text: src_ids [B,T] + src_padding [B,T]
+  const float* src;
+  const int64_t* src_ids;
+  const int64_t* src_length;
+  const float* src_padding;
+  const int64_t* trg_input;            // [B,L]
+  const int64_t* trg;                  // [B,L] (loss) or null
+  const int64_t* trg_length;           // [B]
+  int B, T, L;
+  int training;                        // dropout on
+  uint64_t seed;
+  float loss_scale;                    // multiplies dlogits (1/world for DP mean, gradient-accumulation factor, ...)
+  // outputs (device, optional)
+  float* logits;                       // fp32 [B,L,V]
+  float* loss;                         // [1]
+  float* nll_sum;                      // [B]
+  float* n_tokens;                     // [B]
+  float* enc_out;                      // fp32 [B,T',d]
+};
+
+size_t model_workspace_bytes(const Model& m, int B, int T, int L, int training);
+int model_forward(const Model& m, const Buffers& buf, const Batch& b, bool backward, cudaStream_t st);
+
+// stack-level entry points (layer API; inference/eval forward only)
+// When `need` is non-null the call only reports the workspace bytes it would use (nothing is launched).
+int encoder_forward_api(const Model& m, const Buffers& buf, const float* x, const float* padding, int B, int T, float* out,
+                        int training, uint64_t seed, cudaStream_t st, size_t* need);
+int decoder_forward_api(const Model& m, const Buffers& buf, const float* x, const float* memory, const float* memory_padding,
+                        int B, int L, int Tm, float* out, int training, uint64_t seed, cudaStream_t st, size_t* need);
+int mha_forward_api(const Model& m, const Buffers& buf, const float* query, const float* memory, const float* bias, int B, int Tq,
+                    int Tk, float* out, cudaStream_t st, size_t* need);
+
+uint64_t dropout_stream_id(const std::string& site);
+
+}  // namespace b200st

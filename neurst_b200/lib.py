@@ -56,6 +56,7 @@ def load(build_if_missing=True):
     lib.b200st_last_error.restype = C.c_char_p
     lib.b200st_version.restype = C.c_int
     lib.b200st_launch_count.restype = C.c_int64
+    _declare(lib)
     _lib = lib
     return lib
 
@@ -137,3 +138,82 @@ def gemm_bench(A, B, Cout, iters=50, **kw):
     ms = C.c_float(0)
     check(load().b200st_gemm_bench(C.byref(g), iters, C.byref(ms), _stream()))
     return ms.value
+
+
+# ------------------------------------------------------------------------------------------------
+# model-level structs (mirror include/b200st.h)
+# ------------------------------------------------------------------------------------------------
+MODEL_SPEECH, MODEL_TEXT, MODEL_ENCODER, MODEL_DECODER, MODEL_MHA = 0, 1, 2, 3, 4
+
+
+class Config(C.Structure):
+    _fields_ = [("model_type", C.c_int32),
+                ("d", C.c_int32), ("heads", C.c_int32), ("ffn", C.c_int32), ("enc_layers", C.c_int32),
+                ("dec_layers", C.c_int32), ("vocab", C.c_int32), ("src_vocab", C.c_int32),
+                ("feat", C.c_int32), ("in_channels", C.c_int32), ("channels", C.c_int32), ("conv_layer_norm", C.c_int32),
+                ("precision", C.c_int32),
+                ("ln_eps", C.c_float), ("attention_dropout", C.c_float), ("ffn_dropout", C.c_float),
+                ("postprocess_dropout", C.c_float), ("label_smoothing", C.c_float),
+                ("share_src_trg_embedding", C.c_int32),
+                ("mha_self", C.c_int32), ("mha_din", C.c_int32), ("mha_dmem", C.c_int32), ("mha_dout", C.c_int32),
+                ("with_cross_attention", C.c_int32)]
+
+
+class Buffers(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("shadow", C.c_void_p), ("grads", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_ids", C.c_void_p), ("src_length", C.c_void_p), ("src_padding", C.c_void_p),
+                ("trg_input", C.c_void_p), ("trg", C.c_void_p), ("trg_length", C.c_void_p),
+                ("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32), ("training", C.c_int32),
+                ("seed", C.c_uint64), ("loss_scale", C.c_float),
+                ("logits", C.c_void_p), ("loss", C.c_void_p), ("nll_sum", C.c_void_p), ("n_tokens", C.c_void_p),
+                ("enc_out", C.c_void_p)]
+
+
+# every symbol include/b200st.h declares (tests/test_abi.py checks the .so exports all of them)
+EXPORTS = [
+    "b200st_last_error", "b200st_version", "b200st_launch_count", "b200st_gemm", "b200st_gemm_bench", "b200st_debug_tc",
+    "b200st_create", "b200st_destroy", "b200st_param_arena_numel", "b200st_param_count", "b200st_param_info",
+    "b200st_workspace_bytes", "b200st_forward", "b200st_forward_backward", "b200st_refresh_shadow", "b200st_adam_step",
+    "b200st_encoder_forward", "b200st_decoder_forward", "b200st_mha_forward", "b200st_lsce", "b200st_layernorm_fwd",
+    "b200st_layernorm_bwd", "b200st_conv1_ln_relu_fwd", "b200st_dropout_stream_id", "b200st_dropout_mask",
+]
+
+
+def _declare(lib):
+    lib.b200st_param_arena_numel.restype = C.c_int64
+    lib.b200st_param_arena_numel.argtypes = [C.c_void_p]
+    lib.b200st_param_count.restype = C.c_int32
+    lib.b200st_param_count.argtypes = [C.c_void_p]
+    lib.b200st_workspace_bytes.restype = C.c_int64
+    lib.b200st_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.b200st_dropout_stream_id.restype = C.c_uint64
+    lib.b200st_dropout_stream_id.argtypes = [C.c_char_p]
+    lib.b200st_destroy.argtypes = [C.c_void_p]
+    lib.b200st_param_info.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    lib.b200st_forward.argtypes = [C.c_void_p, C.POINTER(Buffers), C.POINTER(Batch), C.c_void_p]
+    lib.b200st_forward_backward.argtypes = [C.c_void_p, C.POINTER(Buffers), C.POINTER(Batch), C.c_void_p]
+    lib.b200st_refresh_shadow.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.b200st_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_int64, C.c_float, C.c_int32, C.c_void_p]
+    lib.b200st_encoder_forward.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.b200st_decoder_forward.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p,
+                                           C.POINTER(C.c_uint64)]
+    lib.b200st_mha_forward.argtypes = [C.c_void_p, C.POINTER(Buffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.b200st_lsce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p]
+    lib.b200st_layernorm_fwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.b200st_layernorm_bwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_int32, C.c_int32, C.c_void_p]
+    lib.b200st_dropout_mask.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+    lib.b200st_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.b200st_gemm_bench.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.POINTER(C.c_float), C.c_void_p]

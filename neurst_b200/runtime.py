@@ -1,0 +1,189 @@
+"""Device-side state of one model replica: the C handle, the flat parameter / gradient / Adam arenas, the
+bf16 shadow and the workspace.  PyTorch supplies device memory and streams only; all compute is libb200st."""
+import ctypes as C
+
+import torch
+
+from neurst_b200 import lib as L
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def make_config(model_type, d, heads, ffn=0, enc_layers=0, dec_layers=0, vocab=0, src_vocab=0, feat=80, in_channels=1,
+                channels=0, conv_layer_norm=True, precision="bf16", ln_eps=1e-6, attention_dropout=0.0, ffn_dropout=0.0,
+                postprocess_dropout=0.0, label_smoothing=0.0, share_src_trg_embedding=False, mha_self=False, mha_din=0,
+                mha_dmem=0, mha_dout=0, with_cross_attention=True):
+    c = L.Config()
+    c.model_type = model_type
+    c.d, c.heads, c.ffn, c.enc_layers, c.dec_layers = d, heads, ffn, enc_layers, dec_layers
+    c.vocab, c.src_vocab = vocab, src_vocab
+    c.feat, c.in_channels, c.channels, c.conv_layer_norm = feat, in_channels, channels, int(conv_layer_norm)
+    c.precision = {"fp32": L.F32, "float32": L.F32, "bf16": L.BF16, "bfloat16": L.BF16}[precision]
+    c.ln_eps = ln_eps
+    c.attention_dropout, c.ffn_dropout, c.postprocess_dropout = attention_dropout, ffn_dropout, postprocess_dropout
+    c.label_smoothing = label_smoothing
+    c.share_src_trg_embedding = int(share_src_trg_embedding)
+    c.mha_self, c.mha_din, c.mha_dmem, c.mha_dout = int(mha_self), mha_din, mha_dmem, mha_dout
+    c.with_cross_attention = int(with_cross_attention)
+    return c
+
+
+class Runtime:
+    """Owns the handle and the flat arenas of one replica on `device`."""
+
+    def __init__(self, config, device="cuda"):
+        self.lib = L.load()
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.B200STError("neurst_b200 runs on CUDA devices only (no CPU fallback)")
+        h = C.c_void_p()
+        L.check(self.lib.b200st_create(C.byref(config), C.byref(h)))
+        self.handle = h
+        self.bf16 = config.precision == L.BF16
+        self.numel = int(self.lib.b200st_param_arena_numel(h))
+        self.table = {}
+        name = C.create_string_buffer(128)
+        off, nd, shp = C.c_int64(), C.c_int32(), (C.c_int64 * 4)()
+        for i in range(int(self.lib.b200st_param_count(h))):
+            L.check(self.lib.b200st_param_info(h, i, name, 128, C.byref(off), C.byref(nd), shp))
+            self.table[name.value.decode()] = (int(off.value), tuple(int(shp[k]) for k in range(nd.value)))
+        self.params = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        self.shadow = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device) if self.bf16 else None
+        self.grads = None
+        self.adam_m = None
+        self.adam_v = None
+        self.workspace = None
+        self._shadow_stale = True
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.b200st_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- parameters ------------------------------------------------------------------------------
+    def view(self, name, arena=None):
+        off, shp = self.table[name]
+        n = 1
+        for s in shp:
+            n *= s
+        a = self.params if arena is None else arena
+        return a[off:off + n].view(*shp)
+
+    def named_parameters(self):
+        return {k: self.view(k) for k in self.table}
+
+    def load_parameters(self, P):
+        """P: dict name -> tensor/ndarray in the reference's TF layouts (oracle.param_shapes naming)."""
+        for k in self.table:
+            if k not in P:
+                raise KeyError("missing parameter %s" % k)
+            self.view(k).copy_(torch.as_tensor(P[k]).to(torch.float32).reshape(self.table[k][1]))
+        self._shadow_stale = True
+
+    def refresh_shadow(self):
+        if self.bf16:
+            L.check(self.lib.b200st_refresh_shadow(_ptr(self.params), _ptr(self.shadow), self.numel, L._stream()))
+        self._shadow_stale = False
+
+    def ensure_grads(self):
+        if self.grads is None:
+            self.grads = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        return self.grads
+
+    def grad_view(self, name):
+        return self.view(name, self.ensure_grads())
+
+    # ---- execution -------------------------------------------------------------------------------
+    def _workspace(self, nbytes):
+        if self.workspace is None or self.workspace.numel() < nbytes:
+            self.workspace = None
+            self.workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def _buffers(self, nbytes, with_grads):
+        ws = self._workspace(nbytes)
+        base = ws.data_ptr()
+        aligned = (base + 255) // 256 * 256
+        b = L.Buffers()
+        b.params = self.params.data_ptr()
+        b.shadow = self.shadow.data_ptr() if self.bf16 else None
+        b.grads = self.ensure_grads().data_ptr() if with_grads else None
+        b.workspace = aligned
+        b.workspace_bytes = ws.numel() - (aligned - base)
+        return b
+
+    def run(self, batch, backward):
+        """batch: dict of CUDA tensors: src|src_ids, src_length|src_padding, trg_input[, trg, trg_length] (+ opts)."""
+        if self._shadow_stale:
+            self.refresh_shadow()
+        bt = L.Batch()
+        keep = []
+
+        def put(field, t, dtype):
+            if t is None:
+                return
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+            keep.append(t)
+            setattr(bt, field, t.data_ptr())
+
+        trg_input = batch["trg_input"]
+        B, Lq = trg_input.shape
+        if self.config.model_type == L.MODEL_SPEECH:
+            src = batch["src"]
+            T = src.shape[1]
+            put("src", src, torch.float32)
+            put("src_length", batch["src_length"], torch.int64)
+        else:
+            src = batch["src"]
+            T = src.shape[1]
+            put("src_ids", src, torch.int64)
+            put("src_padding", batch["src_padding"], torch.float32)
+        put("trg_input", trg_input, torch.int64)
+        put("trg", batch.get("trg"), torch.int64)
+        put("trg_length", batch.get("trg_length"), torch.int64)
+        bt.B, bt.T, bt.L = B, T, Lq
+        bt.training = int(batch.get("training", backward))
+        bt.seed = int(batch.get("seed", 0))
+        bt.loss_scale = float(batch.get("loss_scale", 1.0))
+        out = {}
+        V = self.config.vocab
+        if batch.get("want_logits", not backward):
+            out["logits"] = torch.empty(B, Lq, V, dtype=torch.float32, device=self.device)
+            bt.logits = out["logits"].data_ptr()
+        if batch.get("trg") is not None:
+            out["loss"] = torch.zeros(1, dtype=torch.float32, device=self.device)
+            out["nll_sum"] = torch.zeros(B, dtype=torch.float32, device=self.device)
+            out["n_tokens"] = torch.zeros(B, dtype=torch.float32, device=self.device)
+            bt.loss, bt.nll_sum, bt.n_tokens = out["loss"].data_ptr(), out["nll_sum"].data_ptr(), out["n_tokens"].data_ptr()
+        if batch.get("want_enc_out", False):
+            Ts = ((T + 1) // 2 + 1) // 2 if self.config.model_type == L.MODEL_SPEECH else T
+            out["enc_out"] = torch.empty(B, Ts, self.config.d, dtype=torch.float32, device=self.device)
+            bt.enc_out = out["enc_out"].data_ptr()
+        need = int(self.lib.b200st_workspace_bytes(self.handle, B, T, Lq, int(backward)))
+        if need <= 0:
+            raise L.B200STError("workspace planning failed: " + self.lib.b200st_last_error().decode())
+        bufs = self._buffers(need, backward)
+        fn = self.lib.b200st_forward_backward if backward else self.lib.b200st_forward
+        L.check(fn(self.handle, C.byref(bufs), C.byref(bt), L._stream()))
+        return out
+
+    def adam_step(self, lr, step_t, beta1=0.9, beta2=0.98, eps=1e-9, grad_scale=1.0, zero_grad=True):
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+        L.check(self.lib.b200st_adam_step(_ptr(self.params), _ptr(self.ensure_grads()), _ptr(self.adam_m), _ptr(self.adam_v),
+                                          _ptr(self.shadow), self.numel, lr, beta1, beta2, eps, int(step_t), grad_scale,
+                                          int(zero_grad), L._stream()))
+        self._shadow_stale = False
+
+    def dropout_mask(self, site, n, p, seed):
+        sid = int(self.lib.b200st_dropout_stream_id(site.encode()))
+        out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        L.check(self.lib.b200st_dropout_mask(int(seed), sid, n, float(p), _ptr(out), L._stream()))
+        return out.bool()

@@ -1,0 +1,96 @@
+"""CUDA path (through the C ABI) vs the oracle and the committed golden fixtures — SpeechTransformer
+forward, loss and every gradient.  fp32 precision is held to the reference's own tolerances; bf16 (tcgen05)
+to the stated looser bounds."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from tests import golden_utils as G
+from tests import parity_utils as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["refpt_speech_toy", "refpt_speech_small"])
+def test_forward_matches_reference_pt_fixture_fp32(name):
+    """logits of the UNMODIFIED reference neurst_pt model (committed fixture) vs CUDA fp32 path."""
+    z, P, cfg = G.refpt_case(name)
+    rt = U.speech_runtime(cfg, "fp32")
+    rt.load_parameters(P)
+    out = rt.run(U.to_cuda(dict(src=G.t(z["src"]), src_length=torch.tensor(z["src_length"]),
+                                trg_input=torch.tensor(z["trg_input"]), want_enc_out=True)), backward=False)
+    err = float((out["logits"].cpu() - G.t(z["logits"])).abs().max())
+    assert err < 1e-4, err          # north_star: logits within 1e-3 of the reference
+
+
+def test_forward_bf16_vs_reference_fixture():
+    z, P, cfg = G.refpt_case("refpt_speech_small")
+    rt = U.speech_runtime(cfg, "bf16")
+    rt.load_parameters(P)
+    out = rt.run(U.to_cuda(dict(src=G.t(z["src"]), src_length=torch.tensor(z["src_length"]),
+                                trg_input=torch.tensor(z["trg_input"]))), backward=False)
+    ref = G.t(z["logits"])
+    err = float((out["logits"].cpu() - ref).abs().max())
+    # bf16 tensor-core operands (8-bit mantissa) through 2+2 layers: stated tolerance 5e-2 abs on O(1) logits
+    assert err < 5e-2, err
+
+
+@pytest.mark.parametrize("precision,tol_logits,tol_grad", [("fp32", 1e-4, 2e-4), ("bf16", 6e-2, 6e-2)])
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_forward_backward_vs_oracle(precision, tol_logits, tol_grad, dropout):
+    cfg = dict(model="speech", d=64, heads=4, enc_layers=2, dec_layers=2, ffn=128, channels=64, feat=80, in_channels=1, vocab=96)
+    P = R.init_params(cfg, seed=7, random_bias=True)
+    B, T, Lq = 3, 61, 9
+    batch = U.synthetic_speech_batch(cfg, B, T, Lq, seed=3)
+    rt = U.speech_runtime(cfg, precision, dropout=dropout, label_smoothing=0.1)
+    rt.load_parameters(P)
+    seed = 4242
+    cb = U.to_cuda(batch)
+    cb.update(training=dropout > 0, seed=seed, want_logits=True)
+    rt.ensure_grads().zero_()
+    out = rt.run(cb, backward=True)
+    T2 = R.length_after_conv(T)
+    masks = U.dropout_masks(rt, cfg, B, T2, Lq, dropout, seed) if dropout > 0 else R.NO_DROPOUT
+    logits, loss, grads = U.oracle_loss_and_grads(P, cfg, batch, 0.1, masks)
+    assert float((out["logits"].cpu().double() - logits).abs().max()) < tol_logits
+    assert abs(float(out["loss"]) - float(loss)) < tol_logits * max(1.0, abs(float(loss)))
+    nt = batch["trg_length"].clamp(max=Lq).float()
+    assert torch.equal(out["n_tokens"].cpu(), nt)
+    worst = ("", 0.0)
+    for k, g in grads.items():
+        e = U.rel_err(rt.grad_view(k), g)
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < tol_grad, worst
+
+
+def test_kat_text_transformer_toy_fp32():
+    """tests/neurst/models/transformer_test.py:23-665 — TF-generated logits of the 2+2-layer toy Transformer."""
+    from tests.test_oracle import transformer_toy_params
+    from neurst_b200 import lib as L
+    k = G.load("kat_transformer")
+    cfg, P = transformer_toy_params(k)
+    rt = U.text_runtime(cfg, "fp32")
+    rt.load_parameters(P)
+    out = rt.run(U.to_cuda(dict(src=torch.tensor(k["dict:src"], dtype=torch.long), src_padding=G.t(k["dict:src_padding"]),
+                                trg_input=torch.tensor(k["dict:trg_input"], dtype=torch.long))), backward=False)
+    assert float(((out["logits"].cpu().double() - torch.tensor(k["expect:0"])) ** 2).sum()) < 1e-9
+
+
+def test_adam_step_matches_oracle():
+    cfg = dict(R.CONFIGS["speech_transformer_toy"])
+    P = R.init_params(cfg, seed=1, random_bias=True)
+    rt = U.speech_runtime(cfg, "fp32")
+    rt.load_parameters(P)
+    g = torch.Generator().manual_seed(0)
+    grad = torch.randn(rt.numel, generator=g)
+    p0 = rt.params.clone().cpu()
+    m = torch.zeros_like(p0); v = torch.zeros_like(p0); p = p0.clone()
+    for t in (1, 2, 3):
+        rt.ensure_grads().copy_(grad.cuda() * t)
+        lr = R.noam_lr(t - 1, 256, 4000, 3.5)
+        rt.adam_step(lr, t, grad_scale=0.5, zero_grad=True)
+        p, m, v = R.adam_update(p, grad * t * 0.5, m, v, lr, t)
+        assert float(rt.grads.abs().max()) == 0.0
+    assert float((rt.params.cpu() - p).abs().max()) < 1e-6
