@@ -138,6 +138,9 @@ int b200st_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, con
 int b200st_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
                          const float* rstd, const float* gamma, const float* beta, const float* dres, void* dx,
                          int32_t dx_dtype, float* dgamma, float* dbeta, int64_t rows, int32_t cols, int32_t relu, void* stream);
+/* softmax over keys with additive [B,Tk] bias / causal mask (multi_head_attention.py:147-160); S fp32 [B,H,Tq,ldS] */
+int b200st_softmax_fwd(const float* S, int64_t ldS, const float* bias_2d, int32_t causal, void* P, int32_t p_dtype,
+                       int64_t ldP, int32_t B, int32_t H, int32_t Tq, int32_t Tk, void* stream);
 /* conv subsampling front-end pieces (audio_modalities.py:84-109) */
 int b200st_conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta,
                              void* y1, int32_t dtype, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t C,

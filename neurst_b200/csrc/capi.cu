@@ -212,6 +212,11 @@ int b200st_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_
   return layernorm_bwd(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, beta, dres, dx, dx_dtype, dgamma, dbeta, rows, cols, relu,
                        reinterpret_cast<cudaStream_t>(stream));
 }
+int b200st_softmax_fwd(const float* S, int64_t ldS, const float* bias_2d, int32_t causal, void* P, int32_t p_dtype,
+                       int64_t ldP, int32_t B, int32_t H, int32_t Tq, int32_t Tk, void* stream) {
+  if (!S || !P) B200ST_FAIL("null argument");
+  return softmax_fwd(S, ldS, bias_2d, causal, P, nullptr, p_dtype, ldP, B, H, Tq, Tk, no_dropout(), reinterpret_cast<cudaStream_t>(stream));
+}
 int b200st_conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta,
                              void* y1, int32_t dtype, int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t C,
                              int32_t use_ln, void* stream) {

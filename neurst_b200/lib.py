@@ -179,7 +179,7 @@ EXPORTS = [
     "b200st_create", "b200st_destroy", "b200st_param_arena_numel", "b200st_param_count", "b200st_param_info",
     "b200st_workspace_bytes", "b200st_forward", "b200st_forward_backward", "b200st_refresh_shadow", "b200st_adam_step",
     "b200st_encoder_forward", "b200st_decoder_forward", "b200st_mha_forward", "b200st_lsce", "b200st_layernorm_fwd",
-    "b200st_layernorm_bwd", "b200st_conv1_ln_relu_fwd", "b200st_dropout_stream_id", "b200st_dropout_mask",
+    "b200st_layernorm_bwd", "b200st_softmax_fwd", "b200st_conv1_ln_relu_fwd", "b200st_dropout_stream_id", "b200st_dropout_mask",
 ]
 
 
@@ -214,6 +214,28 @@ def _declare(lib):
     lib.b200st_layernorm_bwd.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_int32, C.c_int32, C.c_void_p]
+    lib.b200st_softmax_fwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.b200st_dropout_mask.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
     lib.b200st_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.b200st_gemm_bench.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.POINTER(C.c_float), C.c_void_p]
+
+
+def softmax(S, P, bias=None, causal=False):
+    """P = softmax(S + bias[b,k] (+ causal mask)) over the last axis; S fp32 [B,H,Tq,Tk] (last dim contiguous)."""
+    B, H, Tq, Tk = S.shape
+    assert S.is_contiguous() and P.is_contiguous()
+    check(load().b200st_softmax_fwd(S.data_ptr(), S.stride(2), bias.data_ptr() if bias is not None else None, int(causal),
+                                    P.data_ptr(), _dt(P), P.stride(2), B, H, Tq, Tk, _stream()))
+    return P
+
+
+def layernorm(x, gamma, beta, eps, out_dtype=None, relu=False):
+    """LayerNorm over the last axis of a contiguous tensor (fp32 or bf16 in, fp32/bf16 out)."""
+    import torch
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    check(load().b200st_layernorm_fwd(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), _dt(y),
+                                      None, None, rows, cols, int(relu), _stream()))
+    return y

@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference model / criterion API on top of libb200st.
+
+  SpeechTransformer          neurst/models/speech_transformer.py:27-280  (PT twin neurst_pt/models/speech_transformer.py)
+  Transformer                neurst/models/transformer.py:27-260         (cfg-1 plumbing model)
+  LabelSmoothedCrossEntropy  neurst/criterions/label_smoothed_cross_entropy.py:26-157
+
+`Model.new(args, src_meta, trg_meta)` takes the reference's flat `model.params` dict (the yaml / hparams_set keys);
+`forward(inputs, is_training)` takes the reference's input dict (neurst/tasks/speech2text.py:135-161) and returns
+logits [B, L, V].  Training uses the fused `forward_backward(inputs)` entry (loss + all gradients in one C call).
+"""
+import torch
+
+from neurst_b200 import lib as L
+from neurst_b200.runtime import Runtime, make_config
+
+
+def speech_transformer_hparams(name):
+    """neurst/models/speech_transformer.py:190-282 (`build_model_args_by_name`)."""
+    table = {
+        "speech_transformer_toy": dict(dmodel=8, heads=2, enc=2, dec=2, ffn=10, channels=5),
+        "speech_transformer_s": dict(dmodel=256, heads=4, enc=12, dec=6, ffn=2048, channels=256),
+        "speech_transformer_m": dict(dmodel=512, heads=8, enc=12, dec=6, ffn=2048, channels=256),
+        "speech_transformer_l": dict(dmodel=1024, heads=16, enc=12, dec=6, ffn=4096, channels=512),
+    }
+    if name not in table:
+        return None
+    t = table[name]
+    dmodel, rate = t["dmodel"], 0.1
+    params = {
+        "modality.source.kernel_size": 3, "modality.source.strides": 2, "modality.source.channels": t["channels"],
+        "modality.source.layer_norm": True, "modality.dim": dmodel, "modality.share_embedding_and_softmax_weights": True,
+        "modality.timing": "sinusoids",
+    }
+    for side, nl in (("encoder", t["enc"]), ("decoder", t["dec"])):
+        params.update({side + ".num_layers": nl, side + ".hidden_size": dmodel, side + ".num_attention_heads": t["heads"],
+                       side + ".filter_size": t["ffn"], side + ".attention_dropout_rate": rate,
+                       side + ".attention_type": "dot_product", side + ".ffn_activation": "relu",
+                       side + ".ffn_dropout_rate": rate, side + ".layer_postprocess_dropout_rate": rate})
+    return {
+        "model.class": "SpeechTransformer", "model.params": params,
+        "optimizer.class": "Adam", "optimizer.params": {"epsilon": 1.e-9, "beta_1": 0.9, "beta_2": 0.98},
+        "lr_schedule.class": "noam",
+        "lr_schedule.params": {"initial_factor": 5.0 if dmodel > 256 else 3.5, "end_factor": 2.0 if dmodel > 256 else 1.5,
+                               "dmodel": dmodel, "warmup_steps": 25000, "start_decay_at": 50000, "decay_steps": 50000},
+    }
+
+
+def _check_supported(args, speech):
+    def same(a, b):
+        return args.get(a) == args.get(b)
+    for k in ("num_layers",):
+        pass
+    if not (same("encoder.hidden_size", "decoder.hidden_size") and same("encoder.num_attention_heads",
+                                                                       "decoder.num_attention_heads")
+            and same("encoder.filter_size", "decoder.filter_size")):
+        raise NotImplementedError("libb200st needs identical encoder/decoder hidden, heads and filter sizes")
+    if args.get("modality.dim") != args.get("encoder.hidden_size"):
+        raise NotImplementedError("modality.dim must equal the hidden size")
+    if (args.get("modality.timing") or args.get("modality.target.timing")) != "sinusoids":
+        raise NotImplementedError("only sinusoid position signals are supported")
+    if not args.get("modality.share_embedding_and_softmax_weights", False):
+        raise NotImplementedError("the output layer must share the target embedding (all reference presets do)")
+    for side in ("encoder", "decoder"):
+        if args.get(side + ".ffn_activation", "relu") != "relu" or args.get(side + ".attention_type", "dot_product") != "dot_product":
+            raise NotImplementedError("only relu / dot_product are supported")
+    if speech and (args.get("modality.source.kernel_size", 3) != 3 or args.get("modality.source.strides", 2) != 2):
+        raise NotImplementedError("the conv front-end is 3x3 stride 2 (all reference presets)")
+
+
+class _EncoderDecoder:
+    def __init__(self, args, src_meta, trg_meta, rt):
+        self._args = args
+        self._src_meta = src_meta
+        self._trg_meta = trg_meta
+        self._rt = rt
+        self._step_seed = 0
+
+    args = property(lambda self: self._args)
+    runtime = property(lambda self: self._rt)
+
+    def named_parameters(self):
+        return self._rt.named_parameters()
+
+    def load_parameters(self, P):
+        self._rt.load_parameters(P)
+
+    def init_parameters(self, seed=0):
+        """glorot-uniform kernels, zero biases, LN gamma=1/beta=0, embedding N(0, d^-0.5) (text_modalities.py:73-74)."""
+        g = torch.Generator().manual_seed(seed)
+        P = {}
+        for name, (_, shp) in self._rt.table.items():
+            if name.endswith("emb"):
+                t = torch.randn(shp, generator=g) * (shp[1] ** -0.5)
+            elif name.endswith(".gamma"):
+                t = torch.ones(shp)
+            elif len(shp) == 1:
+                t = torch.zeros(shp)
+            else:
+                rf = shp[0] * shp[1] if len(shp) == 4 else 1
+                lim = (6.0 / (shp[-2] * rf + shp[-1] * rf)) ** 0.5
+                t = (torch.rand(shp, generator=g) * 2 - 1) * lim
+            P[name] = t
+        self._rt.load_parameters(P)
+        return self
+
+    def _batch(self, inputs, is_training, **extra):
+        b = dict(inputs)
+        if "trg_padding" in b and "trg_length" not in b:
+            b["trg_length"] = (1.0 - torch.as_tensor(b["trg_padding"]).float()).sum(-1).long()
+        self._step_seed += 1
+        b.update(training=bool(is_training), seed=b.get("seed", self._step_seed))
+        b.update(extra)
+        return b
+
+    def forward(self, inputs, is_training=True):
+        """Returns the logits tensor [B, L, V] (encoder_decoder_model.py:263-279)."""
+        b = self._batch(inputs, is_training, want_logits=True)
+        b.pop("trg", None)
+        return self._rt.run(b, backward=False)["logits"]
+
+    __call__ = forward
+
+    def evaluate(self, inputs, is_training=False):
+        """logits + criterion outputs (nll_sum [B], n_tokens [B], loss) in one call."""
+        return self._rt.run(self._batch(inputs, is_training, want_logits=True), backward=False)
+
+    def forward_backward(self, inputs, is_training=True, loss_scale=1.0):
+        """loss = sum(nll)/sum(tokens) and d loss / d params accumulated into the gradient arena."""
+        return self._rt.run(self._batch(inputs, is_training, want_logits=False, loss_scale=loss_scale), backward=True)
+
+
+class SpeechTransformer(_EncoderDecoder):
+    """ Defines the Speech Transformer model. """
+
+    @classmethod
+    def build_model_args_by_name(cls, name):
+        return speech_transformer_hparams(name)
+
+    @classmethod
+    def new(cls, args, src_meta, trg_meta, name=None, precision="bf16", label_smoothing=0.0, device="cuda"):
+        _check_supported(args, True)
+        cfg = make_config(
+            L.MODEL_SPEECH, args["encoder.hidden_size"], args["encoder.num_attention_heads"], args["encoder.filter_size"],
+            args["encoder.num_layers"], args["decoder.num_layers"], trg_meta["vocab_size"],
+            feat=src_meta["audio_feature_dim"], in_channels=src_meta["audio_feature_channels"],
+            channels=args.get("modality.source.channels", 256), conv_layer_norm=args.get("modality.source.layer_norm", False),
+            precision=precision, ln_eps=args.get("encoder.layer_postprocess_epsilon", 1e-6),
+            attention_dropout=args.get("encoder.attention_dropout_rate", 0.), ffn_dropout=args.get("encoder.ffn_dropout_rate", 0.),
+            postprocess_dropout=args.get("encoder.layer_postprocess_dropout_rate", 0.), label_smoothing=label_smoothing)
+        return cls(args, src_meta, trg_meta, Runtime(cfg, device))
+
+
+class Transformer(_EncoderDecoder):
+    """ Text Transformer (reference cfg-1 plumbing model). """
+
+    @classmethod
+    def new(cls, args, src_meta, trg_meta, name=None, precision="fp32", label_smoothing=0.0, device="cuda"):
+        _check_supported(args, False)
+        share = bool(args.get("modality.share_source_target_embedding", False))
+        cfg = make_config(
+            L.MODEL_TEXT, args["encoder.hidden_size"], args["encoder.num_attention_heads"], args["encoder.filter_size"],
+            args["encoder.num_layers"], args["decoder.num_layers"], trg_meta["vocab_size"], src_vocab=src_meta["vocab_size"],
+            precision=precision, ln_eps=args.get("encoder.layer_postprocess_epsilon", 1e-6),
+            attention_dropout=args.get("encoder.attention_dropout_rate", 0.), ffn_dropout=args.get("encoder.ffn_dropout_rate", 0.),
+            postprocess_dropout=args.get("encoder.layer_postprocess_dropout_rate", 0.), label_smoothing=label_smoothing,
+            share_src_trg_embedding=share)
+        return cls(args, src_meta, trg_meta, Runtime(cfg, device))
+
+
+class LabelSmoothedCrossEntropy:
+    """ Criterion with the reference's call contract: (model_inp, logits) -> (nll_sum [B], n_samples [1], n_tokens [B]). """
+
+    def __init__(self, args):
+        self._label_smoothing = args["label_smoothing"]
+
+    def __call__(self, model_inp, model_out):
+        import ctypes as C
+        logits = model_out["logits"] if isinstance(model_out, dict) else model_out
+        if not torch.is_tensor(logits):
+            raise ValueError("Not supported type of model_out: {}".format(type(model_out)))
+        logits = logits.float().contiguous().cuda()
+        B, Lq, V = logits.shape
+        trg = torch.as_tensor(model_inp["trg"]).long().contiguous().cuda()
+        length = model_inp.get("trg_length", model_inp.get("length"))
+        if length is None:
+            padding = model_inp.get("trg_padding", model_inp.get("padding"))
+            length = (1.0 - torch.as_tensor(padding).float()).sum(-1)
+        length = torch.as_tensor(length).long().contiguous().cuda()
+        nll = torch.zeros(B, device="cuda")
+        ntok = torch.zeros(B, device="cuda")
+        loss = torch.zeros(1, device="cuda")
+        L.check(L.load().b200st_lsce(logits.data_ptr(), trg.data_ptr(), length.data_ptr(), B, Lq, V, self._label_smoothing,
+                                     nll.data_ptr(), ntok.data_ptr(), loss.data_ptr(), None, 0, 1.0, L._stream()))
+        return nll, torch.tensor([float(B)], device="cuda"), ntok
+
+    def reduce_loss(self, model_inp, model_out):
+        nll_sum, _, n_tokens = self(model_inp, model_out)
+        return nll_sum.sum() / n_tokens.sum()
