@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — audio-frames/sec (fwd+bwd[+all-reduce]+Adam) of SpeechTransformer-base on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (libb200st)
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm's CPU path (oracle port)
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # one rank per GPU, NCCL
+
+Workload (BASELINE.json configs[1]): speech_transformer_s (conv2d subsample + 12 enc / 6 dec,
+d=256, ffn=2048, V=8192), synthetic fbank [32,1000,80] per GPU, L=88, dropout 0.1, label smoothing 0.1, bf16 tensor-core
+operands with fp32 accumulation / residual stream / statistics / loss / Adam.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(hparams="speech_transformer_s", B=32, T=1000, F=80, L=88, V=8192)
+# 2*M*N*K of every contraction, fwd+bwd = 3x fwd, padded positions counted
+MFLOP_PER_FRAME = 53.24
+
+
+def flops_per_step(B, T, L, V=8192, d=256, H=4, ffn=2048, C=256, F=80, enc=12, dec=6):
+    T1, F1 = (T + 1) // 2, (F + 1) // 2
+    T2, F2 = (T1 + 1) // 2, (F1 + 1) // 2
+    M, Md, dh = B * T2, B * L, d // H
+    fwd = 2 * 9 * 1 * C * B * T1 * F1 + 2 * 9 * C * C * B * T2 * F2 + 2 * M * (F2 * C) * d
+    fwd += enc * (2 * M * d * 3 * d + 2 * M * d * d + 4 * B * H * T2 * T2 * dh + 4 * M * d * ffn)
+    fwd += dec * (2 * Md * d * 4 * d + 4 * B * H * L * L * dh)
+    fwd += dec * (2 * Md * d * 2 * d + 2 * M * d * 2 * d + 4 * B * H * L * T2 * dh)
+    fwd += dec * 4 * Md * d * ffn + 2 * Md * d * V
+    return 3.0 * fwd
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(tflops_sustained=j.get("bf16_tflops_sustained"), tflops_burst=j.get("bf16_tflops"), hbm_gbs=j.get("hbm_gbs"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on host cores (oracle port — the reference's TF2 path cannot run: no TF wheel,
+# and /root/reference does not exist on the GPU box; its PyTorch mirror has no working backward)
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(B, T, L, steps, warmup, threads):
+    import torch
+    from oracle import restatement as R
+    torch.set_num_threads(threads)
+    cfg = dict(R.CONFIGS["speech_transformer_s"])
+    P = R.init_params(cfg, seed=1234)
+    for v in P.values():
+        v.requires_grad_(True)
+    from neurst_b200.trainer import synthetic_batch
+    batch = synthetic_batch(B, T, L, cfg["vocab"], seed=1234)
+    g = torch.Generator().manual_seed(7)
+
+    def masks():
+        d, H, f = cfg["d"], cfg["heads"], cfg["ffn"]
+        T2 = R.length_after_conv(T)
+        m = {}
+
+        def mk(name, shape):
+            m[name] = torch.rand(shape, generator=g) >= 0.1
+        mk("enc.in_drop", (B, T2, d)); mk("dec.in_drop", (B, L, d))
+        for i in range(cfg["enc_layers"]):
+            mk("enc.%d.att.attn_drop" % i, (B, H, T2, T2)); mk("enc.%d.att.post_drop" % i, (B, T2, d))
+            mk("enc.%d.ffn.ffn_drop" % i, (B, T2, f)); mk("enc.%d.ffn.post_drop" % i, (B, T2, d))
+        for i in range(cfg["dec_layers"]):
+            mk("dec.%d.self.attn_drop" % i, (B, H, L, L)); mk("dec.%d.self.post_drop" % i, (B, L, d))
+            mk("dec.%d.cross.attn_drop" % i, (B, H, L, T2)); mk("dec.%d.cross.post_drop" % i, (B, L, d))
+            mk("dec.%d.ffn.ffn_drop" % i, (B, L, f)); mk("dec.%d.ffn.post_drop" % i, (B, L, d))
+        return R.Masks(0.1, m)
+
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        logits = R.speech_transformer_forward(P, cfg, batch["src"], batch["src_length"], batch["trg_input"], masks())
+        loss = R.reduce_loss(logits, batch["trg"], batch["trg_length"], 0.1)
+        grads = torch.autograd.grad(loss, list(P.values()))
+        with torch.no_grad():   # Adam-free SGD touch so the step is not optimised away; Adam cost is negligible on CPU
+            for p_, g_ in zip(P.values(), grads):
+                p_.sub_(1e-9 * g_)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    times.sort()
+    return times[len(times) // 2], float(loss.detach())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0))
+    B = 2
+    T, L = WORKLOAD["T"], WORKLOAD["L"]
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    sec, _ = cpu_reference_step_time(B, T, L, steps, warmup, threads)
+    val = B * T / sec
+    sample = "oracle port (fp32 torch-CPU restatement of the reference graph) fwd+bwd, B=%d x T=%d frames per step, " \
+             "median of %d steps after %d warm-up" % (B, T, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "audio_frames_per_sec_fwd_bwd", "value": val, "unit": "frames/s", "n_gpus": 0,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "speech_transformer_s fbank[%d,%d,80] L=%d V=8192 (bounded CPU sample of cfg-2)" % (B, T, L)},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from neurst_b200 import lib
+    from neurst_b200.trainer import build_speech_transformer_trainer, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib.load()
+    B, T, L, V = WORKLOAD["B"], WORKLOAD["T"], WORKLOAD["L"], WORKLOAD["V"]
+    trainer, _ = build_speech_transformer_trainer(WORKLOAD["hparams"], V, precision="bf16", label_smoothing=0.1, seed=1234)
+    dev = torch.device("cuda", local_rank)
+
+    # resident-input arm: a few distinct batches already in HBM (activations per step ~4 GB >> 126 MB L2)
+    n_batches = 4
+    dev_batches = [synthetic_batch(B, T, L, V, seed=1234 + rank * 100 + i, device=dev) for i in range(n_batches)]
+    host_batches = [synthetic_batch(B, T, L, V, seed=1234 + rank * 100 + i, pin=True) for i in range(n_batches)]
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    losses = []
+
+    def resident_step(i):
+        losses.append(trainer.train_step(dev_batches[i % n_batches], seed=i + 1))
+
+    def e2e_step(i):
+        hb = host_batches[i % n_batches]
+        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        loss = trainer.train_step(db, seed=i + 1)
+        losses.append(float(loss.item()))            # D2H read of the step's loss
+
+    for i in range(max(3, args.warmup)):
+        resident_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.launch_count()
+    ms_total = timed(resident_step, args.steps)
+    launches = lib.launch_count() - launches0
+    sampler.stop_flag = True
+    loss_val = float(losses[-1])
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # roofline pass (not timed): per-launch CUDA events around the tcgen05 GEMM launches of ONE step
+    gemm = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        lib.profile_begin()
+        resident_step(0)
+        torch.cuda.synchronize()
+        gms, gfl, gn = lib.profile_end()
+        gemm = dict(ms=gms, flops=gfl, launches=gn)
+    barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        sec, _ = cpu_reference_step_time(2, T, L, 1, 1, threads)
+        cpu = {"value": 2 * T / sec, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "oracle port fwd+bwd, fp32 torch-CPU, B=2 x T=%d frames, 1 step after 1 warm-up" % T}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    ms_step = ms_total / args.steps
+    frames = world * B * T
+    value = frames / (ms_step * 1e-3)
+    fl = flops_per_step(B, T, L)
+    ach = fl / (ms_step * 1e-3) / 1e12
+    clocks = sampler.summary()
+    line = {
+        "metric": "audio_frames_per_sec_fwd_bwd", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "SpeechTransformer-base (speech_transformer_s: conv2d subsample + 12enc/6dec, d=256) synthetic "
+                               "fbank [32,1000,80] per GPU, L=88, V=8192, dropout 0.1, label_smoothing 0.1, Adam+noam",
+                   "global_batch_frames": frames, "parallelism": "dp%d" % world,
+                   "l2_policy": "inputs+activations per step (~4 GB) exceed the 126 MB L2; 4 rotating input batches",
+                   "loss_last_step": loss_val},
+        "clocks": clocks,
+        "e2e": {"value": frames / (ms_e2e / args.steps * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": ach / peaks["tflops_sustained"], "traffic": None, "peak_source": peaks["source"],
+                     "algorithmic_flops_per_step": fl, "mflop_per_frame": fl / (B * T) / 1e6,
+                     "note": "whole training step (all kernels) against the sustained cuBLAS bf16 peak; "
+                             "tcgen05 GEMM launches alone: see gemm_kernels"},
+    }
+    if gemm and gemm["ms"] > 0:
+        line["roofline"]["gemm_kernels"] = {"launches": gemm["launches"], "ms_per_step": gemm["ms"],
+                                            "tflops": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12,
+                                            "frac_of_peak": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / peaks["tflops_sustained"],
+                                            "share_of_step": gemm["ms"] / ms_step}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when invoked directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        if args.no_cpu_baseline:
+            cmd.append("--no-cpu-baseline")
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,11 @@ int b200st_dropout_mask(uint64_t seed, uint64_t stream_id, int64_t n, float p, u
 /* tests/bench only: time `iters` back-to-back launches of one GEMM with CUDA events on `stream` (no host overhead) */
 int b200st_gemm_bench(const b200st_gemm_args* args, int32_t iters, float* ms_per_iter, void* stream);
 
+/* bench only: per-launch CUDA-event timing of the tcgen05 GEMM launches issued between begin and end
+ * (sum of kernel durations in ms, sum of their algorithmic FLOPs, number of launches) */
+int b200st_profile_begin(void);
+int b200st_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+
 /* tests only: override tcgen05 shared-memory descriptor fields / tile config (0 = default) */
 int b200st_debug_tc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t k_lbo, uint32_t k_sbo, int32_t force_bn,
                     int32_t force_stages, int32_t max_ctas);

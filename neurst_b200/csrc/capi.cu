@@ -77,6 +77,11 @@ static int convert_gemm(const b200st_gemm_args* a, GemmArgs& g) {
   return 0;
 }
 
+int b200st_profile_begin(void) { tc_profile_begin(); return 0; }
+int b200st_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  return tc_profile_end(gemm_ms, gemm_flops, gemm_launches);
+}
+
 int b200st_debug_tc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t k_lbo, uint32_t k_sbo, int32_t force_bn,
                     int32_t force_stages, int32_t max_ctas) {
   TcDebug& d = tc_debug();

@@ -1,9 +1,9 @@
 // tcgen05 / TMEM / TMA bf16 GEMM for sm_100a.
 //
-// Persistent, warp-specialised kernel (one CTA per SM, 192 threads):
+// Persistent, warp-specialised kernel (one CTA per SM, 320 threads):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, 2 stages)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global), 2 warps per TMEM lane quadrant
 // Tile: 128 x BN x 64 (BN in {64,128,256}); operands may be K-major or MN-major (wgrad / PV products),
 // batched through 4-D tensor maps; optional split-K with fp32 RED accumulation.
 //
@@ -23,7 +23,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                  // 64 bf16 = 128 B = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemLimit = 232448;      // 227 KB
 constexpr uint32_t kABytes = BM * BK * 2;
 
@@ -81,7 +81,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 8); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -155,15 +155,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    // warp w may only touch TMEM lanes [32*(w%4), +32); the two warps sharing a quadrant split the columns.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;              // 0 or 1
     const int row_in_tile = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const GemmEpilogue& ep = p.epi;
+    const bool slow_epi = ep.mask_src != nullptr || ep.drop.p > 0.f;
+    const float relu_floor = ep.relu ? 0.f : -INFINITY;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      const int kb0 = t.split * p.kb_per_split;
-      const bool has_work = kb0 < p.kb_total;     // a trailing split may be empty
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const int m = t.m_blk * BM + row_in_tile;
@@ -173,63 +175,102 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t boff_res = (int64_t)t.b2 * ep.res_sb2 + (int64_t)t.b1 * ep.res_sb1;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         const int n0 = t.n_blk * BN + c0;
         if (n0 >= p.N) break;                     // warp-uniform
         uint32_t r[32];
+        __syncwarp();
         ptx::tmem_ld_32x32b_x32(taddr_row + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
-        if (m < p.M && has_work) {
-          float v[32];
+        if (m < p.M) {
+        const bool full = (n0 + 32 <= p.N);
+        float v[32];
+        if (full && !slow_epi) {
+          // ---- fast path: alpha, bias, relu branch-free; residual vectorised ----
+          if (ep.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);   // n0 % 32 == 0, arena 32B-aligned
+            if ((reinterpret_cast<uintptr_t>(b4) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(b4 + j);
+                v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(r[4 * j + 0]), ep.alpha, bb.x), relu_floor);
+                v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), ep.alpha, bb.y), relu_floor);
+                v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), ep.alpha, bb.z), relu_floor);
+                v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), ep.alpha, bb.w), relu_floor);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] = fmaxf(fmaf(__uint_as_float(r[j]), ep.alpha, __ldg(ep.bias + n0 + j)), relu_floor);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) * ep.alpha, relu_floor);
+          }
+          if (ep.residual) {
+            const float* rp = ep.residual + boff_res + (int64_t)m * ep.res_ld + n0;
+            if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(rp) + j);
+                v[4 * j + 0] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(rp + j);
+            }
+          }
+        } else {
+          // ---- general path: relu-mask source, dropout, ragged N ----
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + j;
             const uint64_t e_idx = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n);
             v[j] = (n < p.N) ? gemm_epilogue_value(ep, __uint_as_float(r[j]), m, n, boff_mask, boff_res, e_idx) : 0.f;
           }
-          const int64_t row_off = boff_c + (int64_t)m * p.ldc + n0;
-          const bool full = (n0 + 32 <= p.N);
-          if (p.atomic) {
-            float* c = reinterpret_cast<float*>(p.C) + row_off;
+        }
+        const int64_t row_off = boff_c + (int64_t)m * p.ldc + n0;
+        if (p.atomic) {
+          float* c = reinterpret_cast<float*>(p.C) + row_off;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) atomicAdd(c + j, v[j]);
+        } else if (p.c_dtype == F32) {
+          float* c = reinterpret_cast<float*>(p.C) + row_off;
+          if (ep.accumulate) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) atomicAdd(c + j, v[j]);
-          } else if (p.c_dtype == F32) {
-            float* c = reinterpret_cast<float*>(p.C) + row_off;
-            if (ep.accumulate) {
+              if (n0 + j < p.N) c[j] += v[j];
+          } else if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) c[j] += v[j];
-            } else if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) c[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + row_off;
+          if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) c[j] = v[j];
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(c + j) = pk;
             }
           } else {
-            __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + row_off;
-            if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(c + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) c[j] = __float2bfloat16_rn(v[j]);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) c[j] = __float2bfloat16_rn(v[j]);
           }
         }
+        }  // m < M
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -318,6 +359,11 @@ int make_operand_map(const GemmOperand& op, int rows, int K, int nb1, int nb2, i
 int g_num_sms = 0;
 int64_t g_launches = 0;
 
+// optional per-launch event timing (bench.py roofline pass; off in the timed region)
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+bool g_prof = false;
+std::vector<ProfRec> g_prof_recs;
+
 template <int BN, bool A_MN, bool B_MN>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int grid, size_t smem,
                    cudaStream_t stream) {
@@ -390,7 +436,9 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.splitk = splitk;
   p.atomic = (splitk > 1) ? 1 : 0;
 
-  // ---- BN selection: fewest (waves x tile cost) ----
+  // ---- BN selection: fewest waves x per-tile cycles.  Per k-block a CTA needs max(tensor time, L2->smem fill time):
+  // 4 MMAs of 128 x c x 16 take 2c cycles; the operand bytes (16 KB + 128c B) arrive at ~44 B/cycle/SM (measured:
+  // profiles/r01_gemm_shapes.md); the epilogue (~10 cycles per output column) overlaps the next tile's main loop.
   int bn = dbg.force_bn;
   if (bn == 0) {
     double best = 1e30;
@@ -399,7 +447,10 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
       if (c > 64 && c >= 2 * ((g.N + 63) / 64 * 64)) continue;   // do not pad N by 2x or more
       int64_t tiles = batch * p.m_tiles * ceil_div(g.N, c) * splitk;
       int64_t waves = (tiles + num_sms - 1) / num_sms;
-      double cost = (double)waves * ((double)c * p.kb_per_split + 96.0 + 0.5 * c);
+      const double fill = (16384.0 + 128.0 * c) / 44.0, mma = 2.0 * c;
+      const double mainloop = p.kb_per_split * (fill > mma ? fill : mma);
+      const double epi = 10.0 * c + 600.0;
+      double cost = (double)waves * ((mainloop > epi ? mainloop : epi) + 800.0);
       if (cost < best) { best = cost; bn = c; }
     }
   }
@@ -434,12 +485,47 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
 
   const int grid = (int)(p.num_tiles < num_sms ? p.num_tiles : num_sms);
   ++g_launches;
+  ProfRec rec{};
+  if (g_prof) {
+    B200ST_CUDA(cudaEventCreate(&rec.e0));
+    B200ST_CUDA(cudaEventCreate(&rec.e1));
+    rec.flops = 2.0 * (double)g.M * g.N * g.K * (double)batch;
+    B200ST_CUDA(cudaEventRecord(rec.e0, stream));
+  }
+  int rc = 0;
   switch (bn) {
-    case 64: return launch_bn<64>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream);
-    case 128: return launch_bn<128>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream);
-    case 256: return launch_bn<256>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream);
+    case 64: rc = launch_bn<64>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream); break;
+    case 128: rc = launch_bn<128>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream); break;
+    case 256: rc = launch_bn<256>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream); break;
     default: B200ST_FAIL("unsupported BN");
   }
+  if (g_prof && rc == 0) {
+    B200ST_CUDA(cudaEventRecord(rec.e1, stream));
+    g_prof_recs.push_back(rec);
+  }
+  return rc;
+}
+
+void tc_profile_begin() {
+  for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof_recs.clear();
+  g_prof = true;
+}
+int tc_profile_end(double* ms, double* flops, int64_t* launches) {
+  g_prof = false;
+  double tms = 0, tf = 0;
+  for (auto& r : g_prof_recs) {
+    B200ST_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    B200ST_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    tms += t; tf += r.flops;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  if (ms) *ms = tms;
+  if (flops) *flops = tf;
+  if (launches) *launches = (int64_t)g_prof_recs.size();
+  g_prof_recs.clear();
+  return 0;
 }
 
 }  // namespace b200st

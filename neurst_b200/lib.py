@@ -175,7 +175,7 @@ class Batch(C.Structure):
 
 # every symbol include/b200st.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "b200st_last_error", "b200st_version", "b200st_launch_count", "b200st_gemm", "b200st_gemm_bench", "b200st_debug_tc",
+    "b200st_last_error", "b200st_version", "b200st_launch_count", "b200st_gemm", "b200st_gemm_bench", "b200st_debug_tc", "b200st_profile_begin", "b200st_profile_end",
     "b200st_create", "b200st_destroy", "b200st_param_arena_numel", "b200st_param_count", "b200st_param_info",
     "b200st_workspace_bytes", "b200st_forward", "b200st_forward_backward", "b200st_refresh_shadow", "b200st_adam_step",
     "b200st_encoder_forward", "b200st_decoder_forward", "b200st_mha_forward", "b200st_lsce", "b200st_layernorm_fwd",
@@ -239,3 +239,14 @@ def layernorm(x, gamma, beta, eps, out_dtype=None, relu=False):
     check(load().b200st_layernorm_fwd(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(), _dt(y),
                                       None, None, rows, cols, int(relu), _stream()))
     return y
+
+
+def profile_begin():
+    check(load().b200st_profile_begin())
+
+
+def profile_end():
+    """-> (sum of tcgen05 GEMM kernel ms, sum of their algorithmic FLOPs, launches) since profile_begin()."""
+    ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+    check(load().b200st_profile_end(C.byref(ms), C.byref(fl), C.byref(n)))
+    return ms.value, fl.value, n.value

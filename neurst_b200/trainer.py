@@ -1,0 +1,135 @@
+"""Data-parallel training step loop (one process per GPU, NCCL over NVLink only).
+
+Replaces, for the SpeechTransformer hot path, the reference's
+  GradAccumKerasModel.train_step / fit loop      neurst/training/gradaccum_keras_model.py:162-260,441-477
+  gradient aggregation                           neurst/training/hvd_utils.py:48-62 (hvd.Average),
+                                                 neurst/training/distribution_utils.py:73-98 (NcclAllReduce)
+  rank-0 weight broadcast                        neurst/exps/trainer.py:285
+  Adam + noam schedule                           neurst/optimizers/__init__.py:21, schedules/noam_schedule.py:75-97
+  throughput accounting                          neurst/training/callbacks.py:209-238 (src_tokens_per_sec = frames/s)
+
+Semantics kept: each replica normalises its loss by ITS OWN token count (label_smoothed_cross_entropy.py:52-53), the
+gradients are averaged over replicas, every replica applies the identical Adam update.
+"""
+import os
+import time
+
+import torch
+
+from neurst_b200.models import SpeechTransformer, speech_transformer_hparams
+
+
+def noam_learning_rate(step, dmodel, warmup_steps=4000, initial_factor=1.0, end_factor=None, start_decay_at=0,
+                       decay_steps=None):
+    """neurst/optimizers/schedules/noam_schedule.py:75-97 (global_step counted from 0)."""
+    gs = float(step) + 1.0
+    if end_factor is None or start_decay_at is None or decay_steps is None:
+        end_factor, start_decay_at, decay_steps = initial_factor, 0, 1
+    step_factor = max(min(gs - start_decay_at, float(decay_steps)), 0.0)
+    lr = end_factor + (initial_factor - end_factor) * (1.0 - step_factor / float(decay_steps))
+    lr *= dmodel ** -0.5
+    lr *= min(1.0, gs / float(warmup_steps))
+    lr /= max(gs, float(warmup_steps)) ** 0.5
+    return lr
+
+
+class DataParallelTrainer:
+    """One replica of the DP job.  `dist` (torch.distributed, NCCL) is used only for the gradient all-reduce, the
+    initial parameter broadcast and scalar metric reduction."""
+
+    def __init__(self, model, optimizer_params=None, lr_schedule_params=None, update_cycle=1, grad_buckets=1):
+        self.model = model
+        self.rt = model.runtime
+        op = optimizer_params or {}
+        self.beta1, self.beta2, self.eps = op.get("beta_1", 0.9), op.get("beta_2", 0.98), op.get("epsilon", 1e-9)
+        self.lr_params = lr_schedule_params or dict(dmodel=model.runtime.config.d, warmup_steps=4000, initial_factor=1.0)
+        self.update_cycle = int(update_cycle)
+        self.global_step = 0
+        self._micro = 0
+        self.dist = torch.distributed if torch.distributed.is_available() and torch.distributed.is_initialized() else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.rt.ensure_grads().zero_()
+        self.grad_buckets = max(1, int(grad_buckets))
+        self._comm_stream = torch.cuda.Stream() if self.dist else None
+
+    def broadcast_parameters(self):
+        """rank 0 -> all (hvd BroadcastGlobalVariablesCallback, exps/trainer.py:285)."""
+        if self.dist:
+            self.dist.broadcast(self.rt.params, src=0)
+            self.rt._shadow_stale = True
+
+    def _allreduce_grads(self):
+        if not self.dist:
+            return
+        g = self.rt.grads
+        if self.grad_buckets == 1:
+            self.dist.all_reduce(g)          # SUM; the mean's 1/world is folded into the Adam kernel's grad_scale
+            return
+        n = g.numel()
+        step = (n + self.grad_buckets - 1) // self.grad_buckets
+        for i in range(0, n, step):
+            self.dist.all_reduce(g[i:i + step])
+
+    def train_step(self, inputs, seed=None):
+        """fwd + bwd (+ all-reduce + Adam every `update_cycle` micro-batches).  Returns the device loss tensor."""
+        b = dict(inputs)
+        if seed is not None:
+            b["seed"] = seed
+        out = self.model.forward_backward(b, is_training=True, loss_scale=1.0)
+        self._micro += 1
+        if self._micro % self.update_cycle == 0:
+            self._allreduce_grads()
+            lr = noam_learning_rate(self.global_step, **self.lr_params)
+            self.global_step += 1
+            # GradientAccumulator averages over update_cycle (gradaccum_keras_model.py:62-109); hvd.Average over ranks
+            scale = 1.0 / (self.world * self.update_cycle)
+            self.rt.adam_step(lr, self.global_step, self.beta1, self.beta2, self.eps, grad_scale=scale, zero_grad=True)
+        return out["loss"]
+
+
+def build_speech_transformer_trainer(hparams_set="speech_transformer_s", vocab_size=8192, feature_dim=80, precision="bf16",
+                                     label_smoothing=0.1, dropout=None, seed=1234, update_cycle=1, device=None):
+    hp = speech_transformer_hparams(hparams_set)
+    args = dict(hp["model.params"])
+    if dropout is not None:
+        for side in ("encoder", "decoder"):
+            for k in ("attention_dropout_rate", "ffn_dropout_rate", "layer_postprocess_dropout_rate"):
+                args["%s.%s" % (side, k)] = dropout
+    src_meta = {"audio_feature_dim": feature_dim, "audio_feature_channels": 1}
+    trg_meta = {"vocab_size": vocab_size, "eos_id": vocab_size - 1, "bos_id": vocab_size - 2, "unk_id": vocab_size - 3,
+                "pad_id": vocab_size - 1}
+    model = SpeechTransformer.new(args, src_meta, trg_meta, precision=precision, label_smoothing=label_smoothing,
+                                  device=device or "cuda")
+    model.init_parameters(seed)
+    tr = DataParallelTrainer(model, hp["optimizer.params"], hp["lr_schedule.params"], update_cycle=update_cycle)
+    tr.broadcast_parameters()
+    return tr, trg_meta
+
+
+def synthetic_batch(B, T, Lq, vocab_size, feature_dim=80, seed=1234, lengths="full", device="cpu", pin=False):
+    """src ~ N(0,1) (utterance-standardised fbank), zero beyond src_length; trg ~ U{4..V-1} ending in
+    EOS then PAD; trg_input = [BOS, trg[:-1]] (neurst/tasks/speech2text.py:149-160)."""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(B, T, feature_dim, 1, generator=g)
+    if lengths == "full":
+        src_length = torch.full((B,), T, dtype=torch.long)
+    else:
+        src_length = (torch.rand(B, generator=g) * 0.4 * T + 0.6 * T).long().clamp(1, T)
+        for i in range(B):
+            src[i, int(src_length[i]):] = 0.0
+    eos, bos = vocab_size - 1, vocab_size - 2
+    trg = torch.randint(4, vocab_size - 2, (B, Lq), generator=g)
+    trg_length = torch.full((B,), Lq, dtype=torch.long) if lengths == "full" else \
+        (torch.rand(B, generator=g) * 0.4 * Lq + 0.6 * Lq).long().clamp(2, Lq)
+    for i in range(B):
+        n = int(trg_length[i])
+        trg[i, n - 1] = eos
+        trg[i, n:] = eos
+    trg_input = torch.cat([torch.full((B, 1), bos, dtype=torch.long), trg[:, :-1]], dim=1)
+    batch = dict(src=src, src_length=src_length, trg=trg, trg_input=trg_input, trg_length=trg_length)
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
+    return batch
