@@ -89,12 +89,23 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_
   }
   return Philox4{c0, c1, c2, c3};
 }
-// keep-decision for element `e` of dropout site `stream`; keep iff u >= p  (u uniform in [0,1))
+// Dropout keep-decisions come 8 at a time: one Philox call yields 128 bits = 8 x 16-bit uniforms for the elements
+// [8g, 8g+8) of dropout site `stream`; element e is kept iff its u16 >= thresh, thresh = round(p * 65536).
+__host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
+  float t = p * 65536.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t stream, uint64_t group, uint32_t thresh) {
+  const Philox4 r = philox4x32_10(seed, group, stream);
+  uint32_t m = 0;
+  m |= ((r.x & 0xffffu) >= thresh ? 1u : 0u) << 0; m |= ((r.x >> 16) >= thresh ? 1u : 0u) << 1;
+  m |= ((r.y & 0xffffu) >= thresh ? 1u : 0u) << 2; m |= ((r.y >> 16) >= thresh ? 1u : 0u) << 3;
+  m |= ((r.z & 0xffffu) >= thresh ? 1u : 0u) << 4; m |= ((r.z >> 16) >= thresh ? 1u : 0u) << 5;
+  m |= ((r.w & 0xffffu) >= thresh ? 1u : 0u) << 6; m |= ((r.w >> 16) >= thresh ? 1u : 0u) << 7;
+  return m;
+}
 __host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t stream, uint64_t e, float p) {
-  Philox4 r = philox4x32_10(seed, e >> 2, stream);
-  uint32_t bits = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-  float u = (float)(bits >> 8) * (1.0f / 16777216.0f);
-  return u >= p;
+  return (dropout_keep8(seed, stream, e >> 3, dropout_thresh16(p)) >> (e & 7)) & 1u;
 }
 
 struct DropoutSpec {

@@ -65,9 +65,7 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
 // =============================================================================================
 // LayerNorm backward: warp per row for dx; per-lane column partials for dgamma/dbeta, block-reduced
 // =============================================================================================
-constexpr int LN_MAX_COLS_PER_LANE = 32;   // cols <= 1024
-
-template <typename TDY, typename TX, typename TDX>
+template <typename TDY, typename TX, typename TDX, int CPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -78,41 +76,45 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
   __syncthreads();
-  float dg_acc[LN_MAX_COLS_PER_LANE], db_acc[LN_MAX_COLS_PER_LANE];
+  float gam[CPL], bet[CPL], dg_acc[CPL], db_acc[CPL];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) { dg_acc[i] = 0.f; db_acc[i] = 0.f; }
+  for (int i = 0; i < CPL; ++i) {
+    const int c = lane + 32 * i;
+    gam[i] = c < cols ? gamma[c] : 0.f; bet[i] = c < cols ? beta[c] : 0.f;
+    dg_acc[i] = 0.f; db_acc[i] = 0.f;
+  }
   const int64_t warps_total = (int64_t)gridDim.x * nwarps;
   for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += warps_total) {
     const float mu = mean[row], rs = rstd[row];
+    float xh[CPL], d[CPL];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) {
+    for (int i = 0; i < CPL; ++i) {
       const int c = lane + 32 * i;
+      xh[i] = 0.f; d[i] = 0.f;
       if (c < cols) {
-        const float xh = (to_f32(x[row * cols + c]) - mu) * rs;
-        float d = to_f32(dy[row * cols + c]);
-        if (relu && (xh * gamma[c] + beta[c]) <= 0.f) d = 0.f;
-        const float g = d * gamma[c];
-        c1 += g; c2 += g * xh;
-        dg_acc[i] += d * xh; db_acc[i] += d;
+        xh[i] = (to_f32(x[row * cols + c]) - mu) * rs;
+        float dd = to_f32(dy[row * cols + c]);
+        if (relu && (xh[i] * gam[i] + bet[i]) <= 0.f) dd = 0.f;
+        d[i] = dd;
+        const float g = dd * gam[i];
+        c1 += g; c2 += g * xh[i];
+        dg_acc[i] += dd * xh[i]; db_acc[i] += dd;
       }
     }
     c1 = warp_sum(c1) / cols; c2 = warp_sum(c2) / cols;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) {
+    for (int i = 0; i < CPL; ++i) {
       const int c = lane + 32 * i;
       if (c < cols) {
-        const float xh = (to_f32(x[row * cols + c]) - mu) * rs;
-        float d = to_f32(dy[row * cols + c]);
-        if (relu && (xh * gamma[c] + beta[c]) <= 0.f) d = 0.f;
-        float v = rs * (d * gamma[c] - c1 - xh * c2);
+        float v = rs * (d[i] * gam[i] - c1 - xh[i] * c2);
         if (dres) v += dres[row * cols + c];
         dx[row * cols + c] = from_f32<TDX>(v);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAX_COLS_PER_LANE; ++i) {
+  for (int i = 0; i < CPL; ++i) {
     const int c = lane + 32 * i;
     if (c < cols) { atomicAdd(&sm[c], dg_acc[i]); atomicAdd(&sm[cols + c], db_acc[i]); }
   }
@@ -127,12 +129,17 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
                   const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
                   float* dbeta, int64_t rows, int cols, int relu, cudaStream_t s) {
   if (rows == 0) return 0;
-  B200ST_CHECK(cols <= 32 * LN_MAX_COLS_PER_LANE, "layernorm_bwd supports cols <= 1024");
-  const int grid = grid_for(rows, 8 * 16, 148 * 4);
+  B200ST_CHECK(cols <= 1024, "layernorm_bwd supports cols <= 1024");
+  const int grid = grid_for(rows, 8 * 4, 148 * 8);      // ~4 rows per warp, up to 8 blocks per SM
   const size_t smem = 2 * (size_t)cols * sizeof(float);
-  DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,
-      (ln_bwd_kernel<TDY, TX, TDX><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres,
-                                                           (TDX*)dx, dgamma, dbeta, rows, cols, relu)))));
+#define LN_BWD_LAUNCH(CPL)                                                                                              \
+  DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
+      (ln_bwd_kernel<TDY, TX, TDX, CPL><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
+                                                                (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
+  if (cols <= 256) LN_BWD_LAUNCH(8);
+  else if (cols <= 512) LN_BWD_LAUNCH(16);
+  else LN_BWD_LAUNCH(32);
+#undef LN_BWD_LAUNCH
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -143,7 +150,41 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
 // =============================================================================================
 constexpr float kFloatMin = -1.0e9f;   // neurst/utils/compat.py:24
 
-template <typename T>
+// Each lane owns groups of 8 consecutive keys (k = 8*(lane + 32*s) + j): 32-byte loads of S, 16-byte stores of P,
+// one Philox call per group.  Dropout element index = row * ldP + k (ldP = Tk rounded up to 8), so groups never
+// straddle rows.  The row (Tk <= 256*STEPS) lives in registers: S is read exactly once.
+__device__ __forceinline__ float masked_logit(float v, const float* br, int k, int causal, int kmax_visible) {
+  if (br) v += br[k];
+  if (causal && k > kmax_visible) v += kFloatMin;
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ void store8(T* dst, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* dst, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[8]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = pk;
+}
+template <typename T> __device__ __forceinline__ void load8(const T* src, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* src, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[8]) {
+  const uint4 pk = *reinterpret_cast<const uint4*>(src);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+template <typename T, int STEPS>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, int64_t ldS,
                                                            const float* __restrict__ bias, int causal,
                                                            T* __restrict__ P_pre, T* __restrict__ P_drop, int64_t ldP,
@@ -151,40 +192,57 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * Tq;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const uint32_t thresh = dropout_thresh16(drop.p);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
     const int q = (int)(row % Tq);
     const int b = (int)(row / ((int64_t)H * Tq));
     const float* sr = S + row * ldS;
     const float* br = bias ? bias + (int64_t)b * Tk : nullptr;
     const int kmax_visible = q + (Tk - Tq);
+    float v[STEPS][8];
     float mx = -INFINITY;
-    for (int k = lane; k < Tk; k += 32) {
-      float v = sr[k];
-      if (br) v += br[k];
-      if (causal && k > kmax_visible) v += kFloatMin;
-      mx = fmaxf(mx, v);
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int k0 = 8 * (lane + 32 * st);
+      if (k0 < Tk) {
+        load8<float>(sr + k0, v[st]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[st][j] = (k0 + j < Tk) ? masked_logit(v[st][j], br, k0 + j, causal, kmax_visible) : -INFINITY;
+          mx = fmaxf(mx, v[st][j]);
+        }
+      }
     }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int k = lane; k < Tk; k += 32) {
-      float v = sr[k];
-      if (br) v += br[k];
-      if (causal && k > kmax_visible) v += kFloatMin;
-      sum += expf(v - mx);
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int k0 = 8 * (lane + 32 * st);
+      if (k0 < Tk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[st][j] = (k0 + j < Tk) ? expf(v[st][j] - mx) : 0.f; sum += v[st][j]; }
+      }
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    for (int k = lane; k < Tk; k += 32) {
-      float v = sr[k];
-      if (br) v += br[k];
-      if (causal && k > kmax_visible) v += kFloatMin;
-      const float p = expf(v - mx) * inv;
-      P_pre[row * ldP + k] = from_f32<T>(p);
-      if (drop.p > 0.f) {
-        // dropout acts on the stored (rounded) probability so that backward sees identical values
-        const float ps = to_f32(from_f32<T>(p));
-        const bool keep = dropout_keep(drop.seed, drop.stream, (uint64_t)(row * Tk + k), drop.p);
-        P_drop[row * ldP + k] = from_f32<T>(keep ? ps * drop.scale : 0.f);
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int k0 = 8 * (lane + 32 * st);
+      if (k0 < Tk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[st][j] *= inv;
+        store8<T>(P_pre + row * ldP + k0, v[st]);
+        if (drop.p > 0.f) {
+          const uint32_t keep = dropout_keep8(drop.seed, drop.stream, (uint64_t)(row * ldP + k0) >> 3, thresh);
+          float w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // dropout acts on the stored (rounded) probability so that backward sees identical values
+            const float ps = to_f32(from_f32<T>(v[st][j]));
+            w[j] = ((keep >> j) & 1u) ? ps * drop.scale : 0.f;
+          }
+          store8<T>(P_drop + row * ldP + k0, w);
+        }
       }
     }
   }
@@ -194,32 +252,55 @@ int softmax_fwd(const float* S, int64_t ldS, const float* bias, int causal, void
                 int64_t ldP, int B, int H, int Tq, int Tk, DropoutSpec drop, cudaStream_t s) {
   const int64_t rows = (int64_t)B * H * Tq;
   if (rows == 0) return 0;
+  B200ST_CHECK(ldS % 8 == 0 && ldP % 8 == 0 && ldS >= Tk && ldP >= Tk, "softmax needs row strides padded to 8");
+  B200ST_CHECK((reinterpret_cast<uintptr_t>(S) & 31) == 0 && (reinterpret_cast<uintptr_t>(P_pre) & 15) == 0, "softmax alignment");
+  B200ST_CHECK(Tk <= 2048, "softmax supports up to 2048 keys");
   const int grid = grid_for(rows, 8);
-  DISPATCH_DTYPE(p_dtype, T, (softmax_fwd_kernel<T><<<grid, 256, 0, s>>>(S, ldS, bias, causal, (T*)P_pre, (T*)P_drop, ldP,
-                                                                          B, H, Tq, Tk, drop)));
+#define SM_FWD(ST) DISPATCH_DTYPE(p_dtype, T, (softmax_fwd_kernel<T, ST><<<grid, 256, 0, s>>>(S, ldS, bias, causal, (T*)P_pre, \
+                                                                                   (T*)P_drop, ldP, B, H, Tq, Tk, drop)))
+  if (Tk <= 256) SM_FWD(1); else if (Tk <= 512) SM_FWD(2); else if (Tk <= 1024) SM_FWD(4); else SM_FWD(8);
+#undef SM_FWD
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 
-template <typename T>
+template <typename T, int STEPS>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ dP, int64_t ldS,
                                                            const T* __restrict__ P_pre, T* __restrict__ dS, int64_t ldP,
                                                            int64_t rows, int Tk, DropoutSpec drop) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const uint32_t thresh = dropout_thresh16(drop.p);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    float d[STEPS][8], pr[STEPS][8];
     float dot = 0.f;
-    for (int k = lane; k < Tk; k += 32) {
-      float d = dP[row * ldS + k];
-      if (drop.p > 0.f) d = dropout_keep(drop.seed, drop.stream, (uint64_t)(row * Tk + k), drop.p) ? d * drop.scale : 0.f;
-      dot += d * to_f32(P_pre[row * ldP + k]);
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int k0 = 8 * (lane + 32 * st);
+      if (k0 < Tk) {
+        load8<float>(dP + row * ldS + k0, d[st]);
+        load8<T>(P_pre + row * ldP + k0, pr[st]);
+        uint32_t keep = 0xffu;
+        if (drop.p > 0.f) keep = dropout_keep8(drop.seed, drop.stream, (uint64_t)(row * ldP + k0) >> 3, thresh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (k0 + j >= Tk) { d[st][j] = 0.f; pr[st][j] = 0.f; }
+          if (drop.p > 0.f) d[st][j] = ((keep >> j) & 1u) ? d[st][j] * drop.scale : 0.f;
+          dot += d[st][j] * pr[st][j];
+        }
+      }
     }
     dot = warp_sum(dot);
-    for (int k = lane; k < Tk; k += 32) {
-      float d = dP[row * ldS + k];
-      if (drop.p > 0.f) d = dropout_keep(drop.seed, drop.stream, (uint64_t)(row * Tk + k), drop.p) ? d * drop.scale : 0.f;
-      dS[row * ldP + k] = from_f32<T>(to_f32(P_pre[row * ldP + k]) * (d - dot));
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+      const int k0 = 8 * (lane + 32 * st);
+      if (k0 < Tk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = pr[st][j] * (d[st][j] - dot);
+        store8<T>(dS + row * ldP + k0, o);
+      }
     }
   }
 }
@@ -227,8 +308,12 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
 int softmax_bwd(const float* dP, int64_t ldS, const void* P_pre, void* dS, int p_dtype, int64_t ldP, int64_t rows,
                 int Tk, DropoutSpec drop, cudaStream_t s) {
   if (rows == 0) return 0;
+  B200ST_CHECK(ldS % 8 == 0 && ldP % 8 == 0 && Tk <= 2048, "softmax_bwd needs row strides padded to 8 and Tk <= 2048");
   const int grid = grid_for(rows, 8);
-  DISPATCH_DTYPE(p_dtype, T, (softmax_bwd_kernel<T><<<grid, 256, 0, s>>>(dP, ldS, (const T*)P_pre, (T*)dS, ldP, rows, Tk, drop)));
+#define SM_BWD(ST) DISPATCH_DTYPE(p_dtype, T, (softmax_bwd_kernel<T, ST><<<grid, 256, 0, s>>>(dP, ldS, (const T*)P_pre, (T*)dS, \
+                                                                                   ldP, rows, Tk, drop)))
+  if (Tk <= 256) SM_BWD(1); else if (Tk <= 512) SM_BWD(2); else if (Tk <= 1024) SM_BWD(4); else SM_BWD(8);
+#undef SM_BWD
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -238,16 +323,28 @@ int softmax_bwd(const float* dP, int64_t ldS, const void* P_pre, void* dS, int p
 // elementwise: cast + dropout, posenc, fill, param cast
 // =============================================================================================
 template <typename T>
-__global__ void cast_dropout_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n, DropoutSpec drop) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = x[i];
-    if (drop.p > 0.f) v = dropout_keep(drop.seed, drop.stream, (uint64_t)i, drop.p) ? v * drop.scale : 0.f;
-    y[i] = from_f32<T>(v);
+__global__ void __launch_bounds__(256) cast_dropout_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n,
+                                                           DropoutSpec drop) {
+  const uint32_t thresh = dropout_thresh16(drop.p);
+  const int64_t ngroups = (n + 7) / 8;
+  const bool vec = (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t keep = drop.p > 0.f ? dropout_keep8(drop.seed, drop.stream, (uint64_t)g, thresh) : 0xffu;
+    float v[8];
+    if (vec) {
+      load8<float>(x + g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * drop.scale : 0.f;
+      store8<T>(y + g * 8, v);
+    } else {
+      for (int j = 0; j < 8 && g * 8 + j < n; ++j)
+        y[g * 8 + j] = from_f32<T>(((keep >> j) & 1u) ? x[g * 8 + j] * drop.scale : 0.f);
+    }
   }
 }
 int cast_dropout(const float* x, void* y, int y_dtype, int64_t n, DropoutSpec drop, cudaStream_t s) {
   if (n == 0) return 0;
-  DISPATCH_DTYPE(y_dtype, T, (cast_dropout_kernel<T><<<grid_for(n, 256 * 4), 256, 0, s>>>(x, (T*)y, n, drop)));
+  DISPATCH_DTYPE(y_dtype, T, (cast_dropout_kernel<T><<<grid_for((n + 7) / 8, 256), 256, 0, s>>>(x, (T*)y, n, drop)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

@@ -65,12 +65,13 @@ int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 // y1 = relu(LN(conv3x3s2(src) + b)); src fp32 [B,T,F,Cin]; w fp32 HWIO [3,3,Cin,C]; y1 (dtype) [B,T1,F1,C]
 int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
                       void* y1, int y_dtype, int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s);
-int conv1_ln_relu_bwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
-                      const void* y1, const void* dy1, int dtype, float* dw, float* db, float* dgamma, float* dbeta,
-                      int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s);
+// Fused backward of conv1's LN+ReLU fed by conv2's dgrad: dy1 = col2im(dcol) (transpose of im2col), ReLU mask from y1,
+// z1 recomputed from src, dz1 = LN'(dy1) written in `dtype`, col1[pos, 0..K1p) = im2col row of src (zero padded) for the
+// filter-gradient GEMM, and db / dgamma / dbeta accumulated.
+int conv1_bwd_fused(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
+                    const void* y1, const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma,
+                    float* dbeta, int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s);
 // col[(b,t2,f2), (kh,kw,c)] = y1[b, 2*t2+kh-1, 2*f2+kw-1, c] (zero outside)
 int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, cudaStream_t s);
-// dy1[b,t1,f1,c] = sum over taps of dcol (transpose of im2col)
-int col2im_3x3s2(const void* dcol, void* dy1, int dtype, int B, int T1, int F1, int C, cudaStream_t s);
 
 }  // namespace b200st

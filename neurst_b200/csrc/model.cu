@@ -636,7 +636,9 @@ static int speech_front_bwd(Ctx& c, const float* src, const float* dx0, const Fr
   void* dy2 = c.act(R2 * C);
   void* dz2 = c.act(R2 * C);
   void* dcol = c.act(R2 * 9 * C);
-  void* dy1 = c.act(R1 * C);
+  void* dz1 = c.act(R1 * C);
+  const int K1p = (9 * cf.in_channels + 7) / 8 * 8;
+  void* col1 = c.act(R1 * K1p);
   RUN(posenc_bwd(dx0, de0, c.adt, (int64_t)Mx * d, sqrtf((float)d), c.drop(cf.postprocess_dropout, sv.s_in), c.st));
   B200ST_TRY(linear_wgrad(c, sv.y2, (int64_t)sv.F2 * C, de0, d, Mx, sv.F2 * C, d, "src.dense.kernel", "src.dense.bias"));
   GemmEpilogue e0 = gemm_defaults().epi;
@@ -649,10 +651,20 @@ static int speech_front_bwd(Ctx& c, const float* src, const float* dx0, const Fr
   }
   B200ST_TRY(linear_wgrad(c, sv.col, 9 * C, dz2, C, (int)R2, 9 * C, C, "src.conv2.kernel", "src.conv2.bias"));
   B200ST_TRY(linear_dgrad(c, dz2, C, (int)R2, C, 9 * C, "src.conv2.kernel", e0, dcol, c.adt, 9 * C));
-  RUN(col2im_3x3s2(dcol, dy1, c.adt, B, sv.T1, sv.F1, C, c.st));
-  RUN(conv1_ln_relu_bwd(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f, sv.y1,
-                        dy1, c.adt, c.G("src.conv1.kernel"), c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T,
-                        F, cf.in_channels, C, cf.conv_layer_norm, c.st));
+  // fused: col2im gather + ReLU' + LN' (z1 recomputed) -> dz1, fbank im2col rows, db/dgamma/dbeta
+  RUN(conv1_bwd_fused(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f, sv.y1,
+                      dcol, c.adt, dz1, col1, K1p, c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F,
+                      cf.in_channels, C, cf.conv_layer_norm, c.st));
+  {
+    // dW1[9*Cin, C] += col1^T dz1   (split-K tcgen05 GEMM over all B*T1*F1 positions)
+    GemmArgs g = gemm_defaults();
+    g.M = 9 * cf.in_channels; g.N = C; g.K = (int)R1;
+    g.A = GemmOperand{col1, c.adt, 1, K1p, 0, 0};
+    g.B = GemmOperand{dz1, c.adt, 1, C, 0, 0};
+    g.C = c.G("src.conv1.kernel"); g.c_dtype = F32; g.ldc = C;
+    g.epi.accumulate = 1; g.splitk = 0;
+    RUN(gemm(g, c.st));
+  }
   return 0;
 }
 

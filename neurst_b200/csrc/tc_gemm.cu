@@ -162,7 +162,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_in_tile = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const GemmEpilogue& ep = p.epi;
-    const bool slow_epi = ep.mask_src != nullptr || ep.drop.p > 0.f;
+    const bool drop_vec_ok = ep.drop.p == 0.f || (p.N % 8 == 0);       // dropout groups of 8 stay row-aligned
+    const uint32_t drop_thresh = dropout_thresh16(ep.drop.p);
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
@@ -185,8 +186,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (m < p.M) {
         const bool full = (n0 + 32 <= p.N);
         float v[32];
-        if (full && !slow_epi) {
-          // ---- fast path: alpha, bias, relu branch-free; residual vectorised ----
+        const char* mask_row = ep.mask_src
+            ? reinterpret_cast<const char*>(ep.mask_src) + (size_t)(boff_mask + (int64_t)m * ep.mask_ld + n0) * (ep.mask_dtype == BF16 ? 2 : 4)
+            : nullptr;
+        const bool fast = full && drop_vec_ok && ((reinterpret_cast<uintptr_t>(mask_row) & 15) == 0);
+        if (fast) {
+          // ---- fast path: alpha, bias, relu branch-free; mask / dropout / residual vectorised ----
           if (ep.bias) {
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);   // n0 % 32 == 0, arena 32B-aligned
             if ((reinterpret_cast<uintptr_t>(b4) & 15) == 0) {
@@ -206,6 +211,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) * ep.alpha, relu_floor);
+          }
+          if (mask_row) {
+            if (ep.mask_dtype == BF16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(mask_row) + j);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __bfloat1622float2(h[i]);
+                  if (!(f.x > 0.f)) v[8 * j + 2 * i] = 0.f;
+                  if (!(f.y > 0.f)) v[8 * j + 2 * i + 1] = 0.f;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(mask_row) + j);
+                if (!(f.x > 0.f)) v[4 * j] = 0.f;
+                if (!(f.y > 0.f)) v[4 * j + 1] = 0.f;
+                if (!(f.z > 0.f)) v[4 * j + 2] = 0.f;
+                if (!(f.w > 0.f)) v[4 * j + 3] = 0.f;
+              }
+            }
+          }
+          if (ep.drop.p > 0.f) {
+            const uint64_t e0 = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n0);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const uint32_t keep = dropout_keep8(ep.drop.seed, ep.drop.stream, (e0 >> 3) + g8, drop_thresh);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[8 * g8 + j] = ((keep >> j) & 1u) ? v[8 * g8 + j] * ep.drop.scale : 0.f;
+            }
           }
           if (ep.residual) {
             const float* rp = ep.residual + boff_res + (int64_t)m * ep.res_ld + n0;

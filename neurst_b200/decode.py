@@ -24,9 +24,9 @@ def _attend(q, keys, values, H, bias=None):
     qh = q.view(B, Tq, H, dh).permute(0, 2, 1, 3)
     kh = keys.view(B, Tk, H, dh).permute(0, 2, 1, 3)
     vh = values.view(B, Tk, H, dh).permute(0, 2, 1, 3)
-    S = torch.empty(B, H, Tq, Tk, dtype=torch.float32, device=q.device)
+    S = L.padded_scores(B, H, Tq, Tk, torch.float32, q.device)
     L.gemm(qh, kh, S, alpha=dh ** -0.5)
-    P = torch.empty_like(S)
+    P = L.padded_scores(B, H, Tq, Tk, torch.float32, q.device)
     L.softmax(S, P, bias=bias)
     ctx = torch.empty(B, Tq, H, dh, dtype=torch.float32, device=q.device)
     L.gemm(P, vh, ctx.permute(0, 2, 1, 3), b_mn=True)

@@ -138,12 +138,10 @@ class MultiHeadAttention(_B200Layer):
         qh = q.reshape(B, Tq, H, dh).permute(0, 2, 1, 3)
         kh = keys.view(B, Tk, H, dh).permute(0, 2, 1, 3)
         vh = values.view(B, Tk, H, dh).permute(0, 2, 1, 3)
-        S = torch.empty(B, H, Tq, Tk, dtype=torch.float32, device=rt.device)
+        S = L.padded_scores(B, H, Tq, Tk, torch.float32, rt.device)
         L.gemm(qh, kh, S, alpha=dh ** -0.5)
-        if bias is not None:
-            S = S + self._f32(bias).view(B, 1, 1, Tk)
-        Pm = torch.empty_like(S)
-        L.softmax(S, Pm)
+        Pm = L.padded_scores(B, H, Tq, Tk, torch.float32, rt.device)
+        L.softmax(S, Pm, bias=self._f32(bias) if bias is not None else None)
         ctx = torch.empty(B, Tq, H, dh, dtype=torch.float32, device=rt.device)
         L.gemm(Pm, vh, ctx.permute(0, 2, 1, 3), b_mn=True)
         out = torch.empty(B * Tq, self._output_depth, dtype=torch.float32, device=rt.device)

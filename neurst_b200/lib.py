@@ -224,7 +224,8 @@ def _declare(lib):
 def softmax(S, P, bias=None, causal=False):
     """P = softmax(S + bias[b,k] (+ causal mask)) over the last axis; S fp32 [B,H,Tq,Tk] (last dim contiguous)."""
     B, H, Tq, Tk = S.shape
-    assert S.is_contiguous() and P.is_contiguous()
+    assert S.stride(-1) == 1 and P.stride(-1) == 1 and S.stride(2) % 8 == 0 and P.stride(2) % 8 == 0, \
+        "softmax rows must be padded to a multiple of 8 (use padded_scores())"
     check(load().b200st_softmax_fwd(S.data_ptr(), S.stride(2), bias.data_ptr() if bias is not None else None, int(causal),
                                     P.data_ptr(), _dt(P), P.stride(2), B, H, Tq, Tk, _stream()))
     return P
@@ -250,3 +251,10 @@ def profile_end():
     ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
     check(load().b200st_profile_end(C.byref(ms), C.byref(fl), C.byref(n)))
     return ms.value, fl.value, n.value
+
+
+def padded_scores(B, H, Tq, Tk, dtype, device):
+    """[B,H,Tq,Tk] view of a buffer whose rows are padded to a multiple of 8 (softmax / TMA row-stride rule)."""
+    import torch
+    Tkp = (Tk + 7) // 8 * 8
+    return torch.zeros(B, H, Tq, Tkp, dtype=dtype, device=device)[..., :Tk]
