@@ -33,6 +33,18 @@ def noam_learning_rate(step, dmodel, warmup_steps=4000, initial_factor=1.0, end_
     return lr
 
 
+def allreduce_sum_(flat, dist, buckets=1):
+    """In-place SUM all-reduce of the flat gradient arena (NCCL on GPUs; the mean's 1/world is folded into the Adam
+    kernel's grad_scale).  `buckets` > 1 splits the arena into contiguous chunks (launch-latency / overlap knob)."""
+    if buckets <= 1:
+        dist.all_reduce(flat)
+        return
+    n = flat.numel()
+    step = (n + buckets - 1) // buckets
+    for i in range(0, n, step):
+        dist.all_reduce(flat[i:i + step])
+
+
 class DataParallelTrainer:
     """One replica of the DP job.  `dist` (torch.distributed, NCCL) is used only for the gradient all-reduce, the
     initial parameter broadcast and scalar metric reduction."""
@@ -51,7 +63,6 @@ class DataParallelTrainer:
         self.rank = self.dist.get_rank() if self.dist else 0
         self.rt.ensure_grads().zero_()
         self.grad_buckets = max(1, int(grad_buckets))
-        self._comm_stream = torch.cuda.Stream() if self.dist else None
 
     def broadcast_parameters(self):
         """rank 0 -> all (hvd BroadcastGlobalVariablesCallback, exps/trainer.py:285)."""
@@ -60,16 +71,8 @@ class DataParallelTrainer:
             self.rt._shadow_stale = True
 
     def _allreduce_grads(self):
-        if not self.dist:
-            return
-        g = self.rt.grads
-        if self.grad_buckets == 1:
-            self.dist.all_reduce(g)          # SUM; the mean's 1/world is folded into the Adam kernel's grad_scale
-            return
-        n = g.numel()
-        step = (n + self.grad_buckets - 1) // self.grad_buckets
-        for i in range(0, n, step):
-            self.dist.all_reduce(g[i:i + step])
+        if self.dist:
+            allreduce_sum_(self.rt.grads, self.dist, self.grad_buckets)
 
     def train_step(self, inputs, seed=None):
         """fwd + bwd (+ all-reduce + Adam every `update_cycle` micro-batches).  Returns the device loss tensor."""
