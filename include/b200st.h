@@ -97,6 +97,7 @@ typedef struct {
   int32_t B, T, L;
   int32_t training;             /* dropout on */
   uint64_t seed;                /* dropout seed of this step */
+  const uint64_t* seed_dev;     /* optional device-resident seed (read at kernel run time: CUDA-graph replay) */
   float loss_scale;             /* multiplies the loss gradient (0 => 1) */
   float* logits;                /* out, optional: fp32 [B,L,V] */
   float* loss;                  /* out, optional: [1] = sum(nll)/sum(tokens) (label_smoothed_cross_entropy.py:46-53) */

@@ -69,7 +69,7 @@ static int convert_gemm(const b200st_gemm_args* a, GemmArgs& g) {
   g.epi.mask_ld = a->mask_ld; g.epi.mask_sb1 = a->mask_sb1; g.epi.mask_sb2 = a->mask_sb2;
   if (a->dropout_p > 0.f) {
     B200ST_CHECK(a->dropout_p < 1.f, "dropout_p must be < 1");
-    g.epi.drop = DropoutSpec{a->dropout_p, 1.f / (1.f - a->dropout_p), a->dropout_seed, a->dropout_stream};
+    g.epi.drop = DropoutSpec{a->dropout_p, 1.f / (1.f - a->dropout_p), a->dropout_seed, a->dropout_stream, nullptr};
   }
   g.epi.residual = a->residual; g.epi.res_ld = a->res_ld; g.epi.res_sb1 = a->res_sb1; g.epi.res_sb2 = a->res_sb2;
   g.epi.accumulate = a->accumulate;
@@ -140,7 +140,7 @@ static Batch to_batch(const b200st_batch* b) {
   Batch r{};
   r.src = b->src; r.src_ids = b->src_ids; r.src_length = b->src_length; r.src_padding = b->src_padding;
   r.trg_input = b->trg_input; r.trg = b->trg; r.trg_length = b->trg_length;
-  r.B = b->B; r.T = b->T; r.L = b->L; r.training = b->training; r.seed = b->seed; r.loss_scale = b->loss_scale;
+  r.B = b->B; r.T = b->T; r.L = b->L; r.training = b->training; r.seed = b->seed; r.seed_dev = b->seed_dev; r.loss_scale = b->loss_scale;
   r.logits = b->logits; r.loss = b->loss; r.nll_sum = b->nll_sum; r.n_tokens = b->n_tokens; r.enc_out = b->enc_out;
   return r;
 }

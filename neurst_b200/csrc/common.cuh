@@ -113,8 +113,10 @@ struct DropoutSpec {
   float scale;      // 1/(1-p)
   uint64_t seed;
   uint64_t stream;  // unique id of the dropout site (layer, op)
+  const uint64_t* seed_ptr;   // optional device address of the seed (CUDA-graph replay with a fresh seed per step)
 };
-__host__ __device__ __forceinline__ DropoutSpec no_dropout() { return DropoutSpec{0.f, 1.f, 0, 0}; }
+__host__ __device__ __forceinline__ DropoutSpec no_dropout() { return DropoutSpec{0.f, 1.f, 0, 0, nullptr}; }
+__device__ __forceinline__ uint64_t dropout_seed(const DropoutSpec& d) { return d.seed_ptr ? *d.seed_ptr : d.seed; }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -142,6 +142,7 @@ struct Ctx {
   bool dry;        // planning pass: allocate only, launch nothing
   bool training;
   uint64_t seed;
+  const uint64_t* seed_dev = nullptr;
   Arena ar;
   int adt;
   Ctx(const Model& mm, const Buffers& b, cudaStream_t s, bool d) : m(mm), buf(b), st(s), dry(d), training(false), seed(0), adt(mm.adt) {
@@ -153,7 +154,7 @@ struct Ctx {
   float* f32(int64_t n) { return reinterpret_cast<float*>(ar.take((size_t)n * 4)); }
   DropoutSpec drop(float p, uint64_t stream) const {
     if (!training || p <= 0.f) return no_dropout();
-    return DropoutSpec{p, 1.f / (1.f - p), seed, stream};
+    return DropoutSpec{p, 1.f / (1.f - p), seed, stream, seed_dev};
   }
   const ParamInfo* info(const std::string& n) const {
     const int i = m.find(n);
@@ -677,6 +678,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   const int Ms = B * Ts, Md = B * L;
   c.training = b.training != 0;
   c.seed = b.seed;
+  c.seed_dev = b.seed_dev;
   if (backward) B200ST_CHECK(c.buf.grads != nullptr && b.trg != nullptr && b.trg_length != nullptr, "backward needs grads and targets");
   if (c.adt == BF16) B200ST_CHECK(c.buf.shadow != nullptr, "bf16 precision needs the bf16 shadow arena");
 

@@ -68,6 +68,7 @@ struct Batch {
   int B, T, L;
   int training;                        // dropout on
   uint64_t seed;
+  const uint64_t* seed_dev;            // optional: device-resident seed (overrides `seed`)
   float loss_scale;                    // multiplies dlogits (1/world for DP mean, gradient-accumulation factor, ...)
   // outputs (device, optional)
   float* logits;                       // fp32 [B,L,V]

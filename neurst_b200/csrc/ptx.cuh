@@ -39,6 +39,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n"
@@ -50,7 +51,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > 40000000u) __trap();
+    if ((++spins & 0xfffu) == 0) {                    // every 4096 failed polls: 4-second wall-clock guard
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) __trap();
+    }
   }
 }
 

@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200st {
 
@@ -240,7 +241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t e0 = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n0);
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
-              const uint32_t keep = dropout_keep8(ep.drop.seed, ep.drop.stream, (e0 >> 3) + g8, drop_thresh);
+              const uint32_t keep = dropout_keep8(dropout_seed(ep.drop), ep.drop.stream, (e0 >> 3) + g8, drop_thresh);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[8 * g8 + j] = ((keep >> j) & 1u) ? v[8 * g8 + j] * ep.drop.scale : 0.f;
             }
@@ -270,15 +271,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t row_off = boff_c + (int64_t)m * p.ldc + n0;
         if (p.atomic) {
           float* c = reinterpret_cast<float*>(p.C) + row_off;
+          if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) atomicAdd(c + j, v[j]);
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                           "f"(v[j + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) atomicAdd(c + j, v[j]);
+          }
         } else if (p.c_dtype == F32) {
           float* c = reinterpret_cast<float*>(p.C) + row_off;
           if (ep.accumulate) {
+            if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) c[j] += v[j];
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = *reinterpret_cast<float4*>(c + j);
+                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+                *reinterpret_cast<float4*>(c + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) c[j] += v[j];
+            }
           } else if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -398,7 +415,7 @@ int g_num_sms = 0;
 int64_t g_launches = 0;
 
 // optional per-launch event timing (bench.py roofline pass; off in the timed region)
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, batch, bn, splitk, a_mn, b_mn, epi; };
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
 
@@ -528,6 +545,10 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
     B200ST_CUDA(cudaEventCreate(&rec.e0));
     B200ST_CUDA(cudaEventCreate(&rec.e1));
     rec.flops = 2.0 * (double)g.M * g.N * g.K * (double)batch;
+    rec.M = g.M; rec.N = g.N; rec.K = g.K; rec.batch = (int)batch; rec.bn = bn; rec.splitk = splitk;
+    rec.a_mn = g.A.mn_major; rec.b_mn = g.B.mn_major;
+    rec.epi = (g.epi.bias ? 1 : 0) | (g.epi.relu ? 2 : 0) | (g.epi.mask_src ? 4 : 0) | (g.epi.drop.p > 0.f ? 8 : 0) |
+              (g.epi.residual ? 16 : 0) | (g.c_dtype == F32 ? 32 : 0);
     B200ST_CUDA(cudaEventRecord(rec.e0, stream));
   }
   int rc = 0;
@@ -552,13 +573,18 @@ void tc_profile_begin() {
 int tc_profile_end(double* ms, double* flops, int64_t* launches) {
   g_prof = false;
   double tms = 0, tf = 0;
+  FILE* dump = getenv("B200ST_PROFILE_CSV") ? fopen(getenv("B200ST_PROFILE_CSV"), "w") : nullptr;
+  if (dump) fprintf(dump, "M,N,K,batch,bn,splitk,a_mn,b_mn,epi,us,tflops\n");
   for (auto& r : g_prof_recs) {
     B200ST_CUDA(cudaEventSynchronize(r.e1));
     float t = 0.f;
     B200ST_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (dump) fprintf(dump, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", r.M, r.N, r.K, r.batch, r.bn, r.splitk, r.a_mn, r.b_mn, r.epi,
+                      t * 1e3, r.flops / (t * 1e-3) / 1e12);
     tms += t; tf += r.flops;
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
+  if (dump) fclose(dump);
   if (ms) *ms = tms;
   if (flops) *flops = tf;
   if (launches) *launches = (int64_t)g_prof_recs.size();

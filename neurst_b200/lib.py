@@ -168,7 +168,7 @@ class Batch(C.Structure):
     _fields_ = [("src", C.c_void_p), ("src_ids", C.c_void_p), ("src_length", C.c_void_p), ("src_padding", C.c_void_p),
                 ("trg_input", C.c_void_p), ("trg", C.c_void_p), ("trg_length", C.c_void_p),
                 ("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32), ("training", C.c_int32),
-                ("seed", C.c_uint64), ("loss_scale", C.c_float),
+                ("seed", C.c_uint64), ("seed_dev", C.c_void_p), ("loss_scale", C.c_float),
                 ("logits", C.c_void_p), ("loss", C.c_void_p), ("nll_sum", C.c_void_p), ("n_tokens", C.c_void_p),
                 ("enc_out", C.c_void_p)]
 

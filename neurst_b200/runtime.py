@@ -187,3 +187,74 @@ class Runtime:
         out = torch.empty(n, dtype=torch.uint8, device=self.device)
         L.check(self.lib.b200st_dropout_mask(int(seed), sid, n, float(p), _ptr(out), L._stream()))
         return out.bool()
+
+
+class GraphedTrainStep:
+    """CUDA-graph capture of one forward+backward call (b200st_forward_backward) at a fixed (B, T, L).
+
+    All launches of the step (~1800 kernels) are replayed from one graph; inputs live in static device buffers that
+    `__call__` refreshes, and the dropout seed is read by the kernels from a device word (`seed_dev`), so every replay
+    draws fresh masks.  Gradients accumulate into the runtime's gradient arena exactly as in the eager path."""
+
+    def __init__(self, rt, B, T, Lq):
+        cfg = rt.config
+        if cfg.model_type != L.MODEL_SPEECH:
+            raise L.B200STError("GraphedTrainStep supports the SpeechTransformer handle")
+        self.rt, self.B, self.T, self.L = rt, B, T, Lq
+        dev = rt.device
+        self.src = torch.zeros(B, T, cfg.feat, cfg.in_channels, dtype=torch.float32, device=dev)
+        self.src_length = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.trg_input = torch.zeros(B, Lq, dtype=torch.int64, device=dev)
+        self.trg = torch.zeros(B, Lq, dtype=torch.int64, device=dev)
+        self.trg_length = torch.ones(B, dtype=torch.int64, device=dev)
+        self.seed = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.nll_sum = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.n_tokens = torch.zeros(B, dtype=torch.float32, device=dev)
+        need = int(rt.lib.b200st_workspace_bytes(rt.handle, B, T, Lq, 1))
+        if need <= 0:
+            raise L.B200STError("workspace planning failed: " + rt.lib.b200st_last_error().decode())
+        self.bufs = rt._buffers(need, True)
+        bt = L.Batch()
+        bt.src, bt.src_length = self.src.data_ptr(), self.src_length.data_ptr()
+        bt.trg_input, bt.trg, bt.trg_length = self.trg_input.data_ptr(), self.trg.data_ptr(), self.trg_length.data_ptr()
+        bt.B, bt.T, bt.L, bt.training = B, T, Lq, 1
+        bt.seed, bt.seed_dev, bt.loss_scale = 0, self.seed.data_ptr(), 1.0
+        bt.loss, bt.nll_sum, bt.n_tokens = self.loss.data_ptr(), self.nll_sum.data_ptr(), self.n_tokens.data_ptr()
+        self.bt = bt
+        self.graph = None
+
+    def _launch(self):
+        L.check(self.rt.lib.b200st_forward_backward(self.rt.handle, C.byref(self.bufs), C.byref(self.bt), L._stream()))
+
+    def capture(self):
+        rt = self.rt
+        if rt._shadow_stale:
+            rt.refresh_shadow()
+        saved = rt.ensure_grads().clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up outside capture (function attributes, tensor-map cache)
+            self._launch()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch()
+        rt.grads.copy_(saved)                  # discard the warm-up / capture-time accumulation
+        self.graph = g
+        return self
+
+    def __call__(self, batch, seed):
+        if self.graph is None:
+            self.capture()
+        if self.rt._shadow_stale:
+            self.rt.refresh_shadow()
+        self.src.copy_(batch["src"], non_blocking=True)
+        self.src_length.copy_(batch["src_length"], non_blocking=True)
+        self.trg_input.copy_(batch["trg_input"], non_blocking=True)
+        self.trg.copy_(batch["trg"], non_blocking=True)
+        self.trg_length.copy_(batch["trg_length"], non_blocking=True)
+        self.seed.fill_(int(seed))
+        self.graph.replay()
+        return {"loss": self.loss, "nll_sum": self.nll_sum, "n_tokens": self.n_tokens}

@@ -49,7 +49,8 @@ class DataParallelTrainer:
     """One replica of the DP job.  `dist` (torch.distributed, NCCL) is used only for the gradient all-reduce, the
     initial parameter broadcast and scalar metric reduction."""
 
-    def __init__(self, model, optimizer_params=None, lr_schedule_params=None, update_cycle=1, grad_buckets=1):
+    def __init__(self, model, optimizer_params=None, lr_schedule_params=None, update_cycle=1, grad_buckets=1,
+                 use_cuda_graph=False):
         self.model = model
         self.rt = model.runtime
         op = optimizer_params or {}
@@ -63,6 +64,8 @@ class DataParallelTrainer:
         self.rank = self.dist.get_rank() if self.dist else 0
         self.rt.ensure_grads().zero_()
         self.grad_buckets = max(1, int(grad_buckets))
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs = {}
 
     def broadcast_parameters(self):
         """rank 0 -> all (hvd BroadcastGlobalVariablesCallback, exps/trainer.py:285)."""
@@ -79,7 +82,15 @@ class DataParallelTrainer:
         b = dict(inputs)
         if seed is not None:
             b["seed"] = seed
-        out = self.model.forward_backward(b, is_training=True, loss_scale=1.0)
+        if self.use_cuda_graph:
+            from neurst_b200.runtime import GraphedTrainStep
+            key = (b["src"].shape[0], b["src"].shape[1], b["trg_input"].shape[1])   # one graph per shape bucket
+            if key not in self._graphs:
+                self._graphs[key] = GraphedTrainStep(self.rt, *key).capture()
+            self._seed_ctr = getattr(self, "_seed_ctr", 0) + 1
+            out = self._graphs[key](b, b.get("seed", self._seed_ctr))
+        else:
+            out = self.model.forward_backward(b, is_training=True, loss_scale=1.0)
         self._micro += 1
         if self._micro % self.update_cycle == 0:
             self._allreduce_grads()
@@ -92,7 +103,7 @@ class DataParallelTrainer:
 
 
 def build_speech_transformer_trainer(hparams_set="speech_transformer_s", vocab_size=8192, feature_dim=80, precision="bf16",
-                                     label_smoothing=0.1, dropout=None, seed=1234, update_cycle=1, device=None):
+                                     label_smoothing=0.1, dropout=None, seed=1234, update_cycle=1, device=None, use_cuda_graph=False):
     hp = speech_transformer_hparams(hparams_set)
     args = dict(hp["model.params"])
     if dropout is not None:
@@ -105,7 +116,8 @@ def build_speech_transformer_trainer(hparams_set="speech_transformer_s", vocab_s
     model = SpeechTransformer.new(args, src_meta, trg_meta, precision=precision, label_smoothing=label_smoothing,
                                   device=device or "cuda")
     model.init_parameters(seed)
-    tr = DataParallelTrainer(model, hp["optimizer.params"], hp["lr_schedule.params"], update_cycle=update_cycle)
+    tr = DataParallelTrainer(model, hp["optimizer.params"], hp["lr_schedule.params"], update_cycle=update_cycle,
+                             use_cuda_graph=use_cuda_graph)
     tr.broadcast_parameters()
     return tr, trg_meta
 

@@ -68,6 +68,7 @@ def _batch(cfg, seed):
 
 
 def _worker(rank, world, port, q):
+    torch.set_num_threads(2)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = dict(R.CONFIGS["speech_transformer_toy"])
@@ -89,7 +90,7 @@ def test_two_rank_data_parallel_matches_manual_average():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
     for p in procs:
         p.join(60)
     assert res[0][2] == 2 and res[1][2] == 2
