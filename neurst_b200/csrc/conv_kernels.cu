@@ -90,36 +90,37 @@ __device__ __forceinline__ void store_row(T* p, int lane, int C, const float (&v
   }
 }
 
-// z[i] = bias + sum_taps x * w  for the lane's channels; weights in registers when CIN1.
+// z[i] = bias + sum_taps x * w  for the lane's channels.  The filter ([9*Cin][C] fp32) and bias live in shared memory
+// (registers are needed for occupancy: these kernels are latency-bound on global loads).
 template <bool VEC, int CPL, bool CIN1>
 struct ConvTaps {
-  float wreg[CIN1 ? 9 : 1][CPL];
-  float breg[CPL];
-  __device__ __forceinline__ void init(const float* __restrict__ w, const float* __restrict__ bias, int lane, int C) {
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      const int c = chan<VEC>(lane, i);
-      breg[i] = c < C ? bias[c] : 0.f;
-      if (CIN1) {
-#pragma unroll
-        for (int tp = 0; tp < 9; ++tp) wreg[tp][i] = c < C ? w[tp * C + c] : 0.f;
-      }
-    }
+  const float* sw;      // smem [9*Cin][C]
+  const float* sb;      // smem [C]
+  __device__ __forceinline__ void init(float* smem, const float* __restrict__ w, const float* __restrict__ bias, int Cin, int C) {
+    const int nw = 9 * Cin * C;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) smem[i] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) smem[nw + i] = bias[i];
+    sw = smem; sb = smem + nw;
+    __syncthreads();
   }
   // xv: the 9*Cin input taps of this position (zero outside), in (kh,kw,ci) order
-  __device__ __forceinline__ void apply(const float* __restrict__ w, const float* xv, int lane, int Cin, int C, float (&z)[CPL]) const {
+  __device__ __forceinline__ void apply(const float* xv, int lane, int Cin, int C, float (&z)[CPL]) const {
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) z[i] = breg[i];
+    for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); z[i] = c < C ? sb[c] : 0.f; }
     if (CIN1) {
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp)
+      for (int tp = 0; tp < 9; ++tp) {
+        const float x = xv[tp];
+        const float* wr = sw + tp * C;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) z[i] = fmaf(xv[tp], wreg[tp][i], z[i]);
+        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, wr[c], z[i]); }
+      }
     } else {
       for (int k = 0; k < 9 * Cin; ++k) {
         const float x = xv[k];
+        const float* wr = sw + k * C;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, __ldg(&w[k * C + c]), z[i]); }
+        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, wr[c], z[i]); }
       }
     }
   }
@@ -151,13 +152,14 @@ __device__ __forceinline__ void ln_stats(const float (&z)[CPL], int lane, int C,
 // conv1 + LN + ReLU forward
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool VEC, int CPL, bool CIN1>
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ src, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, (CPL <= 8 ? 3 : 1)) conv1_fwd_kernel(const float* __restrict__ src, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, T* __restrict__ y, int B,
                                                          int Tn, int F, int Cin, int C, int T1, int F1, int use_ln) {
+  extern __shared__ float conv_smem[];
   const int lane = threadIdx.x & 31;
   ConvTaps<VEC, CPL, CIN1> taps;
-  taps.init(w, bias, lane, C);
+  taps.init(conv_smem, w, bias, CIN1 ? 1 : Cin, C);
   float greg[CPL], bereg[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
     float xv[CIN1 ? 9 : MAX_TAPS];
     gather_taps(src, b, t1, f1, Tn, F, CIN1 ? 1 : Cin, xv);
     float z[CPL];
-    taps.apply(w, xv, lane, Cin, C, z);
+    taps.apply(xv, lane, Cin, C, z);
     if (use_ln) {
       float mean, rstd;
       ln_stats<CPL, VEC>(z, lane, C, eps, mean, rstd);
@@ -190,17 +192,17 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
 // fused conv2-dgrad gather (col2im) + ReLU' + LN' of conv1 (recompute) -> dz1, im2col of src, db/dgamma/dbeta
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool VEC, int CPL, bool CIN1>
-__global__ void __launch_bounds__(256) conv1_bwd_fused_kernel(
+__global__ void __launch_bounds__(256, (CPL <= 8 ? 2 : 1)) conv1_bwd_fused_kernel(
     const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, const T* __restrict__ y1, const T* __restrict__ dcol, T* __restrict__ dz1,
     T* __restrict__ col1, int K1p, float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn,
     int F, int Cin, int C, int T1, int F1, int T2, int F2, int use_ln) {
-  extern __shared__ float sacc[];   // [3][C] block partials: db | dgamma | dbeta
+  extern __shared__ float conv_smem[];   // filter | bias | [3][C] block partials: db | dgamma | dbeta
+  float* sacc = conv_smem + (9 * (CIN1 ? 1 : Cin) + 1) * C;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   ConvTaps<VEC, CPL, CIN1> taps;
-  taps.init(w, bias, lane, C);
+  taps.init(conv_smem, w, bias, CIN1 ? 1 : Cin, C);
   float greg[CPL], bereg[CPL], a_db[CPL], a_dg[CPL], a_dbe[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) conv1_bwd_fused_kernel(
     gather_taps(src, b, t1, f1, Tn, F, CIN1 ? 1 : Cin, xv);
     if (use_ln) {
       float z[CPL];
-      taps.apply(w, xv, lane, Cin, C, z);
+      taps.apply(xv, lane, Cin, C, z);
       float mean, rstd;
       ln_stats<CPL, VEC>(z, lane, C, eps, mean, rstd);
       float c1 = 0.f, c2 = 0.f;
@@ -334,10 +336,12 @@ int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const fl
   const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
   const int64_t npos = (int64_t)B * T1 * F1;
   if (npos == 0) return 0;
-  const int grid = pick_grid(npos, 8 * 8, 148 * 6);
+  const int grid = pick_grid(npos, 8 * 4, 148 * 12);
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0);
+  const size_t smem = (size_t)(9 * Cin + 1) * C * sizeof(float);
+  B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
 #define FWD(VEC, CPL, CIN1)                                                                                             \
-  DISPATCH_DTYPE(y_dtype, TT, (conv1_fwd_kernel<TT, VEC, CPL, CIN1><<<grid, 256, 0, s>>>(src, w, b, gamma, beta, eps, (TT*)y1, \
+  DISPATCH_DTYPE(y_dtype, TT, (conv1_fwd_kernel<TT, VEC, CPL, CIN1><<<grid, 256, smem, s>>>(src, w, b, gamma, beta, eps, (TT*)y1, \
                                                                                         B, T, F, Cin, C, T1, F1, use_ln)))
   if (vec && C <= 256) { if (Cin == 1) FWD(true, 8, true); else FWD(true, 8, false); }
   else if (vec) { if (Cin == 1) FWD(true, 16, true); else FWD(true, 16, false); }
@@ -357,8 +361,9 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
   const int T1 = (T + 1) / 2, F1 = (F + 1) / 2, T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
   const int64_t npos = (int64_t)B * T1 * F1;
   if (npos == 0) return 0;
-  const int grid = pick_grid(npos, 8 * 8, 148 * 4);
-  const size_t smem = 3 * (size_t)C * sizeof(float);
+  const int grid = pick_grid(npos, 8 * 4, 148 * 8);
+  const size_t smem = (size_t)(9 * Cin + 1 + 3) * C * sizeof(float);
+  B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dz1) & 15) == 0);
 #define BWD(VEC, CPL, CIN1)                                                                                             \

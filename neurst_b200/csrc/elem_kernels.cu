@@ -18,6 +18,30 @@ static inline int grid_for(int64_t work, int per_block, int cap = 148 * 16) {
   return (int)(g > cap ? cap : g);
 }
 
+
+// ---- 4-wide vector access along the feature axis (16-byte fp32 / 8-byte bf16) ------------------------------------
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 pk = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
 // =============================================================================================
 // LayerNorm forward: one warp per row, values cached in registers for cols <= 1024
 // =============================================================================================
@@ -51,12 +75,75 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
   }
 }
 
+// cols % 4 == 0, cols <= 128*NV: each lane owns NV groups of 4 contiguous columns (c = 4*lane + 128*g); row in registers
+template <typename TX, typename TY, int NV>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, TY* __restrict__ y,
+                                                          float* __restrict__ y32, float* __restrict__ mean_out,
+                                                          float* __restrict__ rstd_out, int64_t rows, int cols, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float g[NV][4], bt[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * lane + 128 * i;
+    if (c < cols) { load4<float>(gamma + c, g[i]); load4<float>(beta + c, bt[i]); }
+  }
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    float v[NV][4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < cols) { load4<TX>(x + row * cols + c, v[i]); sum += v[i][0] + v[i][1] + v[i][2] + v[i][3]; }
+    }
+    const float mean = warp_sum(sum) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (4 * lane + 128 * i < cols) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float dl = v[i][j] - mean; sq += dl * dl; }
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / cols + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < cols) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = (v[i][j] - mean) * rstd * g[i][j] + bt[i][j];
+          if (relu) o[j] = fmaxf(o[j], 0.f);
+        }
+        store4<TY>(y + row * cols + c, o);
+        if (y32) store4<float>(y32 + row * cols + c, o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
 int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
                   float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, cudaStream_t s) {
   if (rows == 0) return 0;
-  const int grid = grid_for(rows, 8);
-  DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,
-      (ln_fwd_kernel<TX, TY><<<grid, 256, 0, s>>>((const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))));
+  const int grid = grid_for(rows, 8 * 2);
+  const bool vec = (cols % 4 == 0) && cols <= 1024 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!y32 || (reinterpret_cast<uintptr_t>(y32) & 15) == 0);
+#define LN_FWD_VEC(NV)                                                                                                  \
+  DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,                                                               \
+      (ln_fwd_vec_kernel<TX, TY, NV><<<grid, 256, 0, s>>>((const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))))
+  if (vec && cols <= 256) LN_FWD_VEC(2);
+  else if (vec && cols <= 512) LN_FWD_VEC(4);
+  else if (vec) LN_FWD_VEC(8);
+  else
+    DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,
+        (ln_fwd_kernel<TX, TY><<<grid, 256, 0, s>>>((const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))));
+#undef LN_FWD_VEC
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -125,6 +212,78 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   }
 }
 
+// vector variant: cols % 4 == 0, lane owns NV groups of 4 contiguous columns
+template <typename TDY, typename TX, typename TDX, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ dres, TDX* __restrict__ dx,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
+                                                          int cols, int relu) {
+  extern __shared__ float sm[];   // [2][cols] block partials
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float gam[NV][4], bet[NV][4], dg_acc[NV][4], db_acc[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * lane + 128 * i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gam[i][j] = 0.f; bet[i][j] = 0.f; dg_acc[i][j] = 0.f; db_acc[i][j] = 0.f; }
+    if (c < cols) { load4<float>(gamma + c, gam[i]); load4<float>(beta + c, bet[i]); }
+  }
+  const int64_t warps_total = (int64_t)gridDim.x * nwarps;
+  for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += warps_total) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][4], d[NV][4];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xh[i][j] = 0.f; d[i][j] = 0.f; }
+      if (c < cols) {
+        load4<TX>(x + row * cols + c, xh[i]);
+        load4<TDY>(dy + row * cols + c, d[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          if (relu && (xh[i][j] * gam[i][j] + bet[i][j]) <= 0.f) d[i][j] = 0.f;
+          const float g = d[i][j] * gam[i][j];
+          c1 += g; c2 += g * xh[i][j];
+          dg_acc[i][j] += d[i][j] * xh[i][j]; db_acc[i][j] += d[i][j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / cols; c2 = warp_sum(c2) / cols;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = 4 * lane + 128 * i;
+      if (c < cols) {
+        float o[4];
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (dres) load4<float>(dres + row * cols + c, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rs * (d[i][j] * gam[i][j] - c1 - xh[i][j] * c2) + r[j];
+        store4<TDX>(dx + row * cols + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 4 * lane + 128 * i;
+    if (c < cols) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&sm[c + j], dg_acc[i][j]); atomicAdd(&sm[cols + c + j], db_acc[i][j]); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[c], sm[c]);
+    if (dbeta) atomicAdd(&dbeta[c], sm[cols + c]);
+  }
+}
+
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
                   float* dbeta, int64_t rows, int cols, int relu, cudaStream_t s) {
@@ -136,9 +295,20 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
   DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
       (ln_bwd_kernel<TDY, TX, TDX, CPL><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
                                                                 (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
-  if (cols <= 256) LN_BWD_LAUNCH(8);
+  const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0);
+#define LN_BWD_VEC(NV)                                                                                                  \
+  DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
+      (ln_bwd_vec_kernel<TDY, TX, TDX, NV><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
+                                                                   (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
+  if (vec && cols <= 256) LN_BWD_VEC(2);
+  else if (vec && cols <= 512) LN_BWD_VEC(4);
+  else if (vec) LN_BWD_VEC(8);
+  else if (cols <= 256) LN_BWD_LAUNCH(8);
   else if (cols <= 512) LN_BWD_LAUNCH(16);
   else LN_BWD_LAUNCH(32);
+#undef LN_BWD_VEC
 #undef LN_BWD_LAUNCH
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
@@ -350,6 +520,38 @@ int cast_dropout(const float* x, void* y, int y_dtype, int64_t n, DropoutSpec dr
   return 0;
 }
 
+// db[n] += sum_m dY[m,n].  Vector path: each thread owns 8 contiguous columns (16-byte bf16 / 32-byte fp32 loads), a warp
+// covers 256 columns of one row, the 8 warps of a block stride over rows; partials meet in shared memory, one atomic per
+// (block, column).
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dY, int64_t M, int N, int64_t ld, float* __restrict__ db) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (n0 < N) {
+    for (int64_t m = (int64_t)blockIdx.y * 8 + warp; m < M; m += (int64_t)gridDim.y * 8) {
+      float v[8];
+      load8<T>(dY + m * ld + n0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  const int n = blockIdx.x * 256 + c;
+  if (n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][c];
+    atomicAdd(&db[n], t);
+  }
+}
+
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dY, int64_t M, int N, int64_t ld, float* __restrict__ db) {
   __shared__ float red[8][33];
@@ -368,12 +570,23 @@ __global__ void colsum_kernel(const T* __restrict__ dY, int64_t M, int N, int64_
 }
 int colsum_accum(const void* dY, int dtype, int64_t M, int N, int64_t ld, float* db, cudaStream_t s) {
   if (M == 0 || N == 0) return 0;
-  dim3 block(32, 8);
-  int gy = (int)((M + 255) / 256);
-  if (gy > 64) gy = 64;
-  if (gy < 1) gy = 1;
-  dim3 grid(ceil_div(N, 32), gy);
-  DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, 0, s>>>((const T*)dY, M, N, ld, db)));
+  const int esz = dtype == BF16 ? 2 : 4;
+  const bool vec = (N % 8 == 0) && ((ld * esz) % (8 * esz) == 0) && ((reinterpret_cast<uintptr_t>(dY) & (8 * esz - 1)) == 0);
+  if (vec) {
+    const int gx = ceil_div(N, 256);
+    int gy = (int)((M + 63) / 64);
+    const int cap = (148 * 4 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    DISPATCH_DTYPE(dtype, T, (colsum_vec_kernel<T><<<dim3(gx, gy), 256, 0, s>>>((const T*)dY, M, N, ld, db)));
+  } else {
+    dim3 block(32, 8);
+    int gy = (int)((M + 255) / 256);
+    if (gy > 64) gy = 64;
+    if (gy < 1) gy = 1;
+    dim3 grid(ceil_div(N, 32), gy);
+    DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, 0, s>>>((const T*)dY, M, N, ld, db)));
+  }
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
