@@ -66,6 +66,7 @@ typedef struct {
   int32_t share_src_trg_embedding;
   int32_t mha_self, mha_din, mha_dmem, mha_dout;
   int32_t with_cross_attention;
+  int32_t disable_fused_attention;   /* tests: materialised attention (GEMM + softmax kernels) in bf16 mode */
 } b200st_config;
 
 int b200st_create(const b200st_config* cfg, b200st_handle* out);   /* host object only; no device memory */

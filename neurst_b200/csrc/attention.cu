@@ -1,0 +1,602 @@
+// Fused multi-head attention for sm_100a (head dim 64): S = QK^T and O = PV on tcgen05 with fp32 accumulators in
+// TMEM, operands staged by TMA, online softmax with one thread per query row (TMEM lane), additive key bias /
+// causal mask exactly as the reference (multi_head_attention.py:145-160: logits + bias, FLOAT_MIN = -1e9), Philox
+// dropout on the probabilities (:207-208).  The [B,H,Tq,Tk] score / probability tensors never touch HBM: forward
+// keeps only the per-row log-sum-exp; backward recomputes P from Q, K and the LSE (flash-attention style).
+//
+// forward : grid (q tiles of 128, H, B), 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax.
+// backward: grid (kv blocks of 128, H, B): K_j / V_j resident; loops over q tiles; dK_j, dV_j accumulate in TMEM,
+//           dQ tiles are reduced across kv blocks with fp32 vector RED into a scratch buffer.
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace b200st {
+
+int make_tma_map_bf16(const void* ptr, uint64_t inner, uint64_t rows, int nb1, int nb2, int64_t ld, int64_t sb1, int64_t sb2,
+                      uint32_t box_rows, CUtensorMap* out);
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, DH = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kMaskMin = -1.0e9f;   // neurst/utils/compat.py:24
+constexpr uint32_t kTile16K = 128 * 64 * 2;      // [128 rows x 64 bf16] swizzled tile
+
+struct AttnParams {
+  int B, H, Tq, Tk, Tkp;
+  float alpha;                 // dh^-0.5
+  const float* bias;           // [B, Tk] additive or null
+  int causal;
+  DropoutSpec drop;
+  __nv_bfloat16* ctx; int64_t ctx_ld;     // [B*Tq, H*64]
+  float* lse;                  // [B, H, Tq]  (natural log)
+  // backward only
+  const __nv_bfloat16* dctx; int64_t dctx_ld;
+  float* dq_acc; int64_t dq_ld;           // fp32 [B*Tq, H*64] (zero-initialised by the caller)
+  __nv_bfloat16* dk; int64_t dk_ld;       // [B*Tk, ...] view base already offset to the K columns; + h*64
+  __nv_bfloat16* dv; int64_t dv_ld;
+};
+
+__device__ __forceinline__ float logit(const AttnParams& p, float s, const float* bias_row, int k, int q) {
+  float x = s * p.alpha;
+  if (bias_row) x += __ldg(bias_row + k);
+  if (p.causal && k > q + (p.Tk - p.Tq)) x += kMaskMin;
+  return x;
+}
+
+// byte offset of element (row, col) inside a [128 x 64*NCB] bf16 operand stored as NCB column blocks of
+// [128 rows x 128 B] with the 128B swizzle (16-byte chunk index XOR (row & 7))
+__device__ __forceinline__ uint32_t swz_off(int row, int col) {
+  const int cb = col >> 6, c = col & 63;
+  return (uint32_t)(cb * kTile16K + row * 128 + ((((c >> 3) ^ (row & 7)) & 7) << 4) + ((c & 7) << 1));
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ==============================================================================================================
+// forward
+// ==============================================================================================================
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;                          // 16 KB
+  const uint32_t sK = sQ + kTile16K;                 // 2 x 16 KB
+  const uint32_t sV = sK + 2 * kTile16K;             // 2 x 16 KB
+  const uint32_t sP = sV + 2 * kTile16K;             // 2 x 32 KB
+  const uint32_t bars = sP + 4 * kTile16K;
+  const uint32_t q_full = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto s_full = [&](int s) { return bars + 8u * (5 + s); };
+  auto s_empty = [&](int s) { return bars + 8u * (7 + s); };
+  auto p_full = [&](int s) { return bars + 8u * (9 + s); };
+  auto p_empty = [&](int s) { return bars + 8u * (11 + s); };
+  const uint32_t o_ready = bars + 8u * 13;
+  const uint32_t tmem_slot = bars + 8u * 14;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = (p.Tk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(kv_full(s), 1); ptx::mbar_init(kv_empty(s), 1);
+      ptx::mbar_init(s_full(s), 1); ptx::mbar_init(s_empty(s), 4);
+      ptx::mbar_init(p_full(s), 4); ptx::mbar_init(p_empty(s), 1);
+    }
+    ptx::mbar_init(o_ready, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc_n<512>(tmem_slot); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem;            // 2 x 128 columns
+  const uint32_t tO = tmem + 256;      // 64 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, kTile16K);
+      ptx::tma_load_4d(sQ, &tmQ, q_full, 0, qt * BQ, h, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(kv_empty(st), (((uint32_t)j >> 1) & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(kv_full(st), 2 * kTile16K);
+        ptx::tma_load_4d(sK + st * kTile16K, &tmK, kv_full(st), 0, j * BKV, h, b);
+        ptx::tma_load_4d(sV + st * kTile16K, &tmV, kv_full(st), 0, j * BKV, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::make_idesc_bf16(BKV, 0, 0);    // S[128 x 128] = Q K^T, both K-major
+      const uint32_t idesc_o = ptx::make_idesc_bf16(DH, 0, 1);     // O[128 x 64] += P V, V as MN-major B
+      ptx::mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+        ptx::mbar_wait(kv_full(st), ph);
+        ptx::mbar_wait(s_empty(st), ph ^ 1u);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint64_t da = ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024);
+          const uint64_t db = ptx::make_smem_desc_sw128(sK + st * kTile16K + k * 32, 16, 1024);
+          ptx::mma_f16_ss(tS + st * BKV, da, db, idesc_s, k > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(s_full(st));
+      };
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nblk) issue_s(j + 1);
+        ptx::mbar_wait(p_full(st), ((uint32_t)j >> 1) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t da = ptx::make_smem_desc_sw128(sP + st * 2 * kTile16K + (k >> 2) * kTile16K + (k & 3) * 32, 16, 1024);
+          const uint64_t db = ptx::make_smem_desc_sw128(sV + st * kTile16K + k * 2048, 8192, 1024);
+          ptx::mma_f16_ss(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::mma_commit(kv_empty(st));
+        ptx::mma_commit(p_empty(st));
+        ptx::mma_commit(o_ready);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: one thread per query row ----------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int q = qt * BQ + row;
+    const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
+    const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t thresh = dropout_thresh16(p.drop.p);
+    const uint64_t seed = p.drop.p > 0.f ? dropout_seed(p.drop) : 0ull;
+    float m = -INFINITY, l = 0.f;      // running max (log2 domain) and sum
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = ((uint32_t)j >> 1) & 1u;
+      ptx::mbar_wait(s_full(st), ph);
+      ptx::tc_fence_after();
+      // pass 1: block maximum
+      float bmax = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + st * BKV + c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = j * BKV + c0 + i;
+          if (k < p.Tk) bmax = fmaxf(bmax, logit(p, __uint_as_float(r[i]), bias_row, k, q) * kLog2e);
+        }
+      }
+      const float m_new = fmaxf(m, bmax);
+      const float corr = exp2f(m - m_new);           // 0 on the first block (m = -inf)
+      // rescale the running output once the previous PV product has landed
+      if (j > 0) {
+        ptx::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32b_x32(tO + lane_addr + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          ptx::tmem_st_32x32b_x32(tO + lane_addr + c0, r);
+        }
+        ptx::tmem_st_wait();
+      }
+      // pass 2: probabilities -> bf16 P tile in shared memory (A operand of the PV product)
+      ptx::mbar_wait(p_empty(st), ph ^ 1u);
+      float bsum = 0.f;
+      const uint32_t p_base = sP + st * 2 * kTile16K;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + st * BKV + c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int k0 = j * BKV + c0 + g8 * 8;
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            float pr = 0.f;
+            if (k < p.Tk) pr = exp2f(logit(p, __uint_as_float(r[g8 * 8 + i]), bias_row, k, q) * kLog2e - m_new);
+            bsum += pr;
+            pv[i] = pr;
+          }
+          if (p.drop.p > 0.f) {
+            const uint32_t keep = dropout_keep8(seed, p.drop.stream, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = ((keep >> i) & 1u) ? pv[i] * p.drop.scale : 0.f;
+          }
+          st_shared_v4(p_base + swz_off(row, c0 + g8 * 8), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]),
+                       pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
+        }
+      }
+      l = l * corr + bsum;
+      m = m_new;
+      ptx::fence_proxy_async_smem();       // P (generic-proxy writes) -> visible to the tensor-core (async) proxy
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { ptx::mbar_arrive(s_empty(st)); ptx::mbar_arrive(p_full(st)); }
+    }
+    // ---- epilogue: O / l -> ctx, LSE ----
+    ptx::mbar_wait(o_ready, (uint32_t)(nblk - 1) & 1u);
+    ptx::tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* dst = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(tO + lane_addr + c0, r);
+      ptx::tmem_ld_wait();
+      if (q < p.Tq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
+          pk.y = pack_bf16(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
+          pk.z = pack_bf16(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
+          pk.w = pack_bf16(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+        }
+      }
+    }
+    if (q < p.Tq && p.lse) p.lse[row_g] = m * kLn2 + logf(l);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
+
+// ==============================================================================================================
+// backward: one CTA per (kv block, head, batch)
+// ==============================================================================================================
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base;                          // 16 KB
+  const uint32_t sV = sK + kTile16K;                 // 16 KB
+  const uint32_t sQ = sV + kTile16K;                 // 2 x 16 KB
+  const uint32_t sdO = sQ + 2 * kTile16K;            // 2 x 16 KB
+  const uint32_t sP = sdO + 2 * kTile16K;            // 32 KB  [128 q x 128 keys] as 2 column blocks
+  const uint32_t sdS = sP + 2 * kTile16K;            // 32 KB
+  const uint32_t bars = sdS + 2 * kTile16K;
+  const uint32_t kv_full = bars;
+  auto qdo_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto qdo_empty = [&](int s) { return bars + 8u * (3 + s); };
+  const uint32_t sdp_full = bars + 8u * 5;
+  const uint32_t pds_full = bars + 8u * 6;
+  const uint32_t dq_full = bars + 8u * 7;
+  const uint32_t dq_empty = bars + 8u * 8;
+  const uint32_t tmem_slot = bars + 8u * 9;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nq = (p.Tq + BQ - 1) / BQ;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV); ptx::prefetch_tensormap(&tmdO);
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(qdo_full(s), 1); ptx::mbar_init(qdo_empty(s), 1); }
+    ptx::mbar_init(sdp_full, 1); ptx::mbar_init(pds_full, 4);
+    ptx::mbar_init(dq_full, 1); ptx::mbar_init(dq_empty, 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc_n<512>(tmem_slot); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * kTile16K);
+      ptx::tma_load_4d(sK, &tmK, kv_full, 0, jb * BKV, h, b);
+      ptx::tma_load_4d(sV, &tmV, kv_full, 0, jb * BKV, h, b);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        ptx::mbar_wait(qdo_empty(st), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(qdo_full(st), 2 * kTile16K);
+        ptx::tma_load_4d(sQ + st * kTile16K, &tmQ, qdo_full(st), 0, i * BQ, h, b);
+        ptx::tma_load_4d(sdO + st * kTile16K, &tmdO, qdo_full(st), 0, i * BQ, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = ptx::make_idesc_bf16(BKV, 0, 0);    // [128q x 128k], A,B K-major
+      const uint32_t idesc_kv = ptx::make_idesc_bf16(DH, 1, 1);    // dV/dK [128k x 64] = X^T Y : A, B MN-major
+      const uint32_t idesc_q = ptx::make_idesc_bf16(DH, 0, 1);     // dQ [128q x 64] = dS K : A K-major, B MN-major
+      ptx::mbar_wait(kv_full, 0);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i & 1;
+        const uint32_t q_s = sQ + st * kTile16K, do_s = sdO + st * kTile16K;
+        ptx::mbar_wait(qdo_full(st), ((uint32_t)i >> 1) & 1u);
+        ptx::tc_fence_after();
+        // S = Q K^T ; dP = dO V^T    (S / dP TMEM is free: the compute warps finished tile i-1 before pds_full(i-1))
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          ptx::mma_f16_ss(tS, ptx::make_smem_desc_sw128(q_s + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                          idesc_s, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          ptx::mma_f16_ss(tdP, ptx::make_smem_desc_sw128(do_s + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sV + k * 32, 16, 1024),
+                          idesc_s, k > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(sdp_full);
+        ptx::mbar_wait(pds_full, (uint32_t)i & 1u);
+        ptx::mbar_wait(dq_empty, ((uint32_t)i & 1u) ^ 1u);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k) {       // contraction over the 128 query rows
+          const uint64_t a_p = ptx::make_smem_desc_sw128(sP + k * 2048, 16384, 1024);
+          const uint64_t a_ds = ptx::make_smem_desc_sw128(sdS + k * 2048, 16384, 1024);
+          const uint64_t b_do = ptx::make_smem_desc_sw128(do_s + k * 2048, 8192, 1024);
+          const uint64_t b_q = ptx::make_smem_desc_sw128(q_s + k * 2048, 8192, 1024);
+          ptx::mma_f16_ss(tdV, a_p, b_do, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+          ptx::mma_f16_ss(tdK, a_ds, b_q, idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {      // contraction over the 128 keys
+          const uint64_t a_ds = ptx::make_smem_desc_sw128(sdS + (k >> 2) * kTile16K + (k & 3) * 32, 16, 1024);
+          const uint64_t b_k = ptx::make_smem_desc_sw128(sK + k * 2048, 8192, 1024);
+          ptx::mma_f16_ss(tdQ, a_ds, b_k, idesc_q, k > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(qdo_empty(st));
+        ptx::mma_commit(dq_full);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
+    const uint32_t thresh = dropout_thresh16(p.drop.p);
+    const uint64_t seed = p.drop.p > 0.f ? dropout_seed(p.drop) : 0ull;
+    for (int i = 0; i < nq; ++i) {
+      const int q = i * BQ + row;
+      const bool qv = q < p.Tq;
+      const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
+      // D = rowsum(dO * O), LSE (log2 domain)
+      float Dq = 0.f, lse2 = 0.f;
+      if (qv) {
+        const __nv_bfloat16* o_row = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH;
+        const __nv_bfloat16* do_row = p.dctx + ((int64_t)b * p.Tq + q) * p.dctx_ld + h * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 8) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(o_row + c)), d = __ldg(reinterpret_cast<const uint4*>(do_row + c));
+          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+          const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 x = __bfloat1622float2(ah[t]), y = __bfloat1622float2(dh[t]);
+            Dq += x.x * y.x + x.y * y.y;
+          }
+        }
+        lse2 = p.lse[row_g] * kLog2e;
+      }
+      ptx::mbar_wait(sdp_full, (uint32_t)i & 1u);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t rs[32], rp[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
+        ptx::tmem_ld_32x32b_x32(tdP + lane_addr + c0, rp);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int k0 = jb * BKV + c0 + g8 * 8;
+          uint32_t keep = 0xffu;
+          if (p.drop.p > 0.f) keep = dropout_keep8(seed, p.drop.stream, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
+          float pd[8], ds[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int k = k0 + t;
+            float pr = 0.f, dsv = 0.f, pdv = 0.f;
+            if (qv && k < p.Tk) {
+              pr = exp2f(logit(p, __uint_as_float(rs[g8 * 8 + t]), bias_row, k, q) * kLog2e - lse2);
+              float dpv = __uint_as_float(rp[g8 * 8 + t]);
+              if (p.drop.p > 0.f) {
+                const bool kp = (keep >> t) & 1u;
+                dpv = kp ? dpv * p.drop.scale : 0.f;
+                pdv = kp ? pr * p.drop.scale : 0.f;
+              } else {
+                pdv = pr;
+              }
+              dsv = pr * (dpv - Dq);
+            }
+            pd[t] = pdv; ds[t] = dsv;
+          }
+          const uint32_t off = swz_off(row, c0 + g8 * 8);
+          st_shared_v4(sP + off, pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]), pack_bf16(pd[6], pd[7]));
+          st_shared_v4(sdS + off, pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(pds_full);
+      // ---- dQ tile -> fp32 reduction across kv blocks ----
+      ptx::mbar_wait(dq_full, (uint32_t)i & 1u);
+      ptx::tc_fence_after();
+      float* dq_row = p.dq_acc + ((int64_t)b * p.Tq + q) * p.dq_ld + h * DH;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DH; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tdQ + lane_addr + c0, r);
+        ptx::tmem_ld_wait();
+        if (qv) {
+#pragma unroll
+          for (int t = 0; t < 32; t += 4)
+            red_add_v4(dq_row + c0 + t, __uint_as_float(r[t]) * p.alpha, __uint_as_float(r[t + 1]) * p.alpha,
+                       __uint_as_float(r[t + 2]) * p.alpha, __uint_as_float(r[t + 3]) * p.alpha);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dq_empty);
+    }
+    // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them) ----
+    const int kk = jb * BKV + row;
+    __nv_bfloat16* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH;
+    __nv_bfloat16* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t rv[32], rk[32];
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(tdV + lane_addr + c0, rv);
+      ptx::tmem_ld_32x32b_x32(tdK + lane_addr + c0, rk);
+      ptx::tmem_ld_wait();
+      if (kk < p.Tk) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 a, c;
+          a.x = pack_bf16(__uint_as_float(rv[t]), __uint_as_float(rv[t + 1]));
+          a.y = pack_bf16(__uint_as_float(rv[t + 2]), __uint_as_float(rv[t + 3]));
+          a.z = pack_bf16(__uint_as_float(rv[t + 4]), __uint_as_float(rv[t + 5]));
+          a.w = pack_bf16(__uint_as_float(rv[t + 6]), __uint_as_float(rv[t + 7]));
+          c.x = pack_bf16(__uint_as_float(rk[t]) * p.alpha, __uint_as_float(rk[t + 1]) * p.alpha);
+          c.y = pack_bf16(__uint_as_float(rk[t + 2]) * p.alpha, __uint_as_float(rk[t + 3]) * p.alpha);
+          c.z = pack_bf16(__uint_as_float(rk[t + 4]) * p.alpha, __uint_as_float(rk[t + 5]) * p.alpha);
+          c.w = pack_bf16(__uint_as_float(rk[t + 6]) * p.alpha, __uint_as_float(rk[t + 7]) * p.alpha);
+          *reinterpret_cast<uint4*>(dv_row + c0 + t) = a;
+          *reinterpret_cast<uint4*>(dk_row + c0 + t) = c;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
+constexpr size_t kBwdSmem = 1024 + (size_t)(2 + 2 + 2 + 2 + 2) * kTile16K + 8 * 12 + 64;
+
+// dst(bf16)[r, 0..cols) = src(fp32)[r, 0..cols)   (dq scratch -> the q columns of the fused dqkv buffer)
+__global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
+                                 int64_t rows, int cols) {
+  const int64_t n8 = rows * (cols / 8);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (cols / 8);
+    const int c = (int)(i % (cols / 8)) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src + r * ld_src + c), b2 = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+    uint4 pk;
+    pk.x = pack_bf16(a.x, a.y); pk.y = pack_bf16(a.z, a.w); pk.z = pack_bf16(b2.x, b2.y); pk.w = pack_bf16(b2.z, b2.w);
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = pk;
+  }
+}
+
+constexpr size_t kFwdSmem = 1024 + (size_t)(1 + 2 + 2 + 4) * kTile16K + 8 * 16 + 64;
+
+}  // namespace
+
+// q/k/v: bf16 views [B*T, ld] with head h at columns [h*64, h*64+64)
+int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
+                        int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
+                        cudaStream_t s) {
+  B200ST_CHECK(Tq > 0 && Tk > 0 && B > 0 && H > 0, "empty attention");
+  B200ST_CHECK(B <= 65535 && H <= 65535, "attention grid too large");
+  CUtensorMap tq, tk, tv;
+  B200ST_TRY(make_tma_map_bf16(q, DH, Tq, H, B, q_ld, DH, (int64_t)Tq * q_ld, BQ, &tq));
+  B200ST_TRY(make_tma_map_bf16(k, DH, Tk, H, B, k_ld, DH, (int64_t)Tk * k_ld, BKV, &tk));
+  B200ST_TRY(make_tma_map_bf16(v, DH, Tk, H, B, v_ld, DH, (int64_t)Tk * v_ld, BKV, &tv));
+  AttnParams p{};
+  p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.Tkp = (Tk + 7) / 8 * 8;
+  p.alpha = 0.125f;                     // 64^-0.5 (multi_head_attention.py:203)
+  p.bias = bias; p.causal = causal; p.drop = drop;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx); p.ctx_ld = ctx_ld; p.lse = lse;
+  B200ST_CHECK((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && ctx_ld % 8 == 0, "ctx must be 16-byte aligned");
+  static bool attr = false;
+  if (!attr) {
+    B200ST_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    attr = true;
+  }
+  dim3 grid((Tq + BQ - 1) / BQ, H, B);
+  attn_fwd_kernel<<<grid, 192, kFwdSmem, s>>>(tq, tk, tv, p);
+  tc_count_launch();
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// dq_scratch: fp32 [B*Tq, H*64] (overwritten).  dq/dk/dv: bf16 views like q/k/v.  lse / ctx from the forward pass.
+int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
+                        int64_t ctx_ld, const void* dctx, int64_t dctx_ld, const float* lse, int B, int H, int Tq, int Tk,
+                        const float* bias, int causal, DropoutSpec drop, float* dq_scratch, void* dq, int64_t dq_ld, void* dk,
+                        int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s) {
+  B200ST_CHECK(Tq > 0 && Tk > 0 && B > 0 && H > 0 && B <= 65535 && H <= 65535, "bad attention shape");
+  CUtensorMap tq, tk, tv, tdo;
+  B200ST_TRY(make_tma_map_bf16(q, DH, Tq, H, B, q_ld, DH, (int64_t)Tq * q_ld, BQ, &tq));
+  B200ST_TRY(make_tma_map_bf16(k, DH, Tk, H, B, k_ld, DH, (int64_t)Tk * k_ld, BKV, &tk));
+  B200ST_TRY(make_tma_map_bf16(v, DH, Tk, H, B, v_ld, DH, (int64_t)Tk * v_ld, BKV, &tv));
+  B200ST_TRY(make_tma_map_bf16(dctx, DH, Tq, H, B, dctx_ld, DH, (int64_t)Tq * dctx_ld, BQ, &tdo));
+  AttnParams p{};
+  p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.Tkp = (Tk + 7) / 8 * 8;
+  p.alpha = 0.125f;
+  p.bias = bias; p.causal = causal; p.drop = drop;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ctx)); p.ctx_ld = ctx_ld;
+  p.lse = const_cast<float*>(lse);
+  p.dctx = reinterpret_cast<const __nv_bfloat16*>(dctx); p.dctx_ld = dctx_ld;
+  p.dq_acc = dq_scratch; p.dq_ld = (int64_t)H * DH;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_ld = dk_ld;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_ld = dv_ld;
+  B200ST_CHECK(((reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(dq) |
+                 reinterpret_cast<uintptr_t>(dq_scratch)) & 15) == 0, "attention gradient buffers must be 16-byte aligned");
+  static bool attr = false;
+  if (!attr) {
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    attr = true;
+  }
+  const int64_t rows = (int64_t)B * Tq;
+  B200ST_CUDA(cudaMemsetAsync(dq_scratch, 0, sizeof(float) * (size_t)rows * H * DH, s));
+  dim3 grid((Tk + BKV - 1) / BKV, H, B);
+  attn_bwd_kernel<<<grid, 192, kBwdSmem, s>>>(tq, tk, tv, tdo, p);
+  B200ST_LAUNCH_CHECK();
+  const int64_t n8 = rows * (H * DH / 8);
+  int64_t g = (n8 + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  cast_rows_kernel<<<(int)g, 256, 0, s>>>(dq_scratch, (int64_t)H * DH, reinterpret_cast<__nv_bfloat16*>(dq), dq_ld, rows, H * DH);
+  tc_count_launch();
+  g_kernel_launches += 1;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200st

@@ -108,6 +108,7 @@ int b200st_create(const b200st_config* cfg, b200st_handle* out) {
   c.share_src_trg_embedding = cfg->share_src_trg_embedding;
   c.mha_self = cfg->mha_self; c.mha_din = cfg->mha_din; c.mha_dmem = cfg->mha_dmem; c.mha_dout = cfg->mha_dout;
   c.with_cross_attention = cfg->with_cross_attention;
+  c.disable_fused_attention = cfg->disable_fused_attention;
   if (c.model_type < 0 || c.model_type > MODEL_MHA) { delete h; B200ST_FAIL("unknown model_type"); }
   if (c.attention_dropout < 0 || c.attention_dropout >= 1 || c.ffn_dropout < 0 || c.ffn_dropout >= 1 ||
       c.postprocess_dropout < 0 || c.postprocess_dropout >= 1) { delete h; B200ST_FAIL("dropout rates must be in [0,1)"); }

@@ -82,6 +82,7 @@ struct TcDebug {
 };
 TcDebug& tc_debug();
 int64_t tc_launch_count();
+void tc_count_launch();
 void tc_profile_begin();
 int tc_profile_end(double* ms, double* flops, int64_t* launches);
 

@@ -61,6 +61,17 @@ int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s);
 int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 
+// ---- fused attention (bf16, head dim 64): tcgen05 QK^T / PV with on-chip online softmax (attention.cu) ----
+// q/k/v/ctx/dctx/dq/dk/dv: bf16 views [B*T, ld], head h at columns [h*64, h*64+64); bias fp32 [B,Tk] or null;
+// lse fp32 [B,H,Tq] (written by forward, read by backward); dq_scratch fp32 [B*Tq, H*64].
+int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
+                        int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
+                        cudaStream_t s);
+int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
+                        int64_t ctx_ld, const void* dctx, int64_t dctx_ld, const float* lse, int B, int H, int Tq, int Tk,
+                        const float* bias, int causal, DropoutSpec drop, float* dq_scratch, void* dq, int64_t dq_ld, void* dk,
+                        int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s);
+
 // ---- conv front-end (audio_modalities.py:84-109) ----
 // y1 = relu(LN(conv3x3s2(src) + b)); src fp32 [B,T,F,Cin]; w fp32 HWIO [3,3,Cin,C]; y1 (dtype) [B,T1,F1,C]
 int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,

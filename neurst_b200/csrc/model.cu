@@ -239,8 +239,16 @@ static GemmOperand head_op(const Ctx& c, View v, int T, int dh, int mn_major) {
 }
 static int round8(int x) { return (x + 7) / 8 * 8; }
 
+static bool use_fused_attention(const Ctx& c, const AttnDims& a) {
+  return c.adt == BF16 && a.units / a.H == 64 && !c.m.cfg.disable_fused_attention;
+}
+
 static int attention_fwd(Ctx& c, const AttnDims& a, View q, View k, View v, const float* bias, int causal, DropoutSpec drop,
-                         float* S, void* p_pre, void* p_drop, void* ctx) {
+                         float* S, void* p_pre, void* p_drop, void* ctx, float* lse) {
+  if (use_fused_attention(c, a)) {
+    RUN(attention_fwd_fused(q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, a.B, a.H, a.Tq, a.Tk, bias, causal, drop, ctx, a.units, lse, c.st));
+    return 0;
+  }
   const int dh = a.units / a.H, Tkp = round8(a.Tk);
   GemmArgs g = gemm_defaults();
   g.M = a.Tq; g.N = a.Tk; g.K = dh; g.nb1 = a.H; g.nb2 = a.B;
@@ -261,7 +269,13 @@ static int attention_fwd(Ctx& c, const AttnDims& a, View q, View k, View v, cons
 
 // dctx (act dtype) [B*Tq, units]  ->  dq, dk, dv views (act dtype)
 static int attention_bwd(Ctx& c, const AttnDims& a, View q, View k, View v, const void* p_pre, const void* p_drop,
-                         DropoutSpec drop, const void* dctx, float* dP, void* dS, View dq, View dk, View dv) {
+                         DropoutSpec drop, const void* dctx, float* dP, void* dS, View dq, View dk, View dv, const void* ctx,
+                         const float* lse, const float* bias, int causal, float* dq32) {
+  if (use_fused_attention(c, a)) {
+    RUN(attention_bwd_fused(q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, ctx, a.units, dctx, a.units, lse, a.B, a.H, a.Tq, a.Tk, bias, causal,
+                            drop, dq32, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, c.st));
+    return 0;
+  }
   const int dh = a.units / a.H, Tkp = round8(a.Tk);
   const int64_t psb1 = (int64_t)a.Tq * Tkp, psb2 = (int64_t)a.H * a.Tq * Tkp;
   const float alpha = 1.0f / sqrtf((float)dh);
@@ -308,6 +322,7 @@ struct AttnSave {
   void* qkv = nullptr;      // self: [M,3u]; cross: q [M,u]
   void* kv = nullptr;       // cross: [Mk,2u]
   void* p_pre = nullptr; void* p_drop = nullptr; void* ctx = nullptr;
+  float* lse = nullptr;     // fused attention: per-row log-sum-exp [B,H,Tq]
   const void* mem = nullptr; // cross: memory in act dtype [Mk, d]
   const float* bias = nullptr; int causal = 0;
   AttnDims dims{};
@@ -330,6 +345,7 @@ struct Scratch {   // shared transient buffers (sized for the largest sublayer)
   void* dkv = nullptr;      // [Mk,2d]
   void* dF1 = nullptr;      // [M,ffn]
   float* dh = nullptr;      // [M,d] fp32
+  float* dq32 = nullptr;    // [M,d] fp32 (fused attention: dQ reduction across kv blocks)
 };
 
 // x_out = x_in + dropout(Attn(LN(x_in)))  — pre-norm block (common_layers.py:73-85)
@@ -344,15 +360,19 @@ static int self_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_in
   sv.h = c.act((int64_t)M * d); sv.mean = c.f32(M); sv.rstd = c.f32(M);
   sv.qkv = c.act((int64_t)M * 3 * d);
   const DropoutSpec adrop = c.drop(cf.attention_dropout, sv.s_attn);
-  sv.p_pre = c.act((int64_t)B * cf.heads * T * Tkp);
-  sv.p_drop = adrop.p > 0.f ? c.act((int64_t)B * cf.heads * T * Tkp) : nullptr;
+  if (use_fused_attention(c, sv.dims)) {
+    sv.lse = c.f32((int64_t)B * cf.heads * T);
+  } else {
+    sv.p_pre = c.act((int64_t)B * cf.heads * T * Tkp);
+    sv.p_drop = adrop.p > 0.f ? c.act((int64_t)B * cf.heads * T * Tkp) : nullptr;
+  }
   sv.ctx = c.act((int64_t)M * d);
   RUN(layernorm_fwd(x_in, F32, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), cf.ln_eps, sv.h, c.adt, nullptr, sv.mean, sv.rstd,
                     M, d, 0, c.st));
   GemmEpilogue e0 = gemm_defaults().epi;
   B200ST_TRY(linear_fwd(c, sv.h, d, M, d, 3 * d, pre + ".qkv.kernel", pre + ".qkv.bias", e0, sv.qkv, c.adt, 3 * d));
   View q{sv.qkv, 3 * d}, k{c.act_off(sv.qkv, d), 3 * d}, v{c.act_off(sv.qkv, 2 * d), 3 * d};
-  B200ST_TRY(attention_fwd(c, sv.dims, q, k, v, bias, causal, adrop, sc.S, sv.p_pre, sv.p_drop, sv.ctx));
+  B200ST_TRY(attention_fwd(c, sv.dims, q, k, v, bias, causal, adrop, sc.S, sv.p_pre, sv.p_drop, sv.ctx, sv.lse));
   GemmEpilogue e1 = gemm_defaults().epi;
   e1.drop = c.drop(cf.postprocess_dropout, sv.s_post);
   e1.residual = x_in; e1.res_ld = d;
@@ -370,7 +390,7 @@ static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_o
   View q{sv.qkv, 3 * d}, k{c.act_off(sv.qkv, d), 3 * d}, v{c.act_off(sv.qkv, 2 * d), 3 * d};
   View dq{sc.dqkv, 3 * d}, dk{c.act_off(sc.dqkv, d), 3 * d}, dv{c.act_off(sc.dqkv, 2 * d), 3 * d};
   B200ST_TRY(attention_bwd(c, sv.dims, q, k, v, sv.p_pre, sv.p_drop, c.drop(cf.attention_dropout, sv.s_attn), sc.dctx, sc.S, sc.dS,
-                           dq, dk, dv));
+                           dq, dk, dv, sv.ctx, sv.lse, sv.bias, sv.causal, sc.dq32));
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, 3 * d, M, d, 3 * d, pre + ".qkv.kernel", pre + ".qkv.bias"));
   B200ST_TRY(linear_dgrad(c, sc.dqkv, 3 * d, M, 3 * d, d, pre + ".qkv.kernel", e0, sc.dh, F32, d));
   RUN(layernorm_bwd(sc.dh, F32, sv.x_in, F32, sv.mean, sv.rstd, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), dx_out, dx_in, F32,
@@ -391,8 +411,12 @@ static int cross_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_i
   sv.qkv = c.act((int64_t)M * d);
   sv.kv = c.act((int64_t)Mk * 2 * d);
   const DropoutSpec adrop = c.drop(cf.attention_dropout, sv.s_attn);
-  sv.p_pre = c.act((int64_t)B * cf.heads * L * Tkp);
-  sv.p_drop = adrop.p > 0.f ? c.act((int64_t)B * cf.heads * L * Tkp) : nullptr;
+  if (use_fused_attention(c, sv.dims)) {
+    sv.lse = c.f32((int64_t)B * cf.heads * L);
+  } else {
+    sv.p_pre = c.act((int64_t)B * cf.heads * L * Tkp);
+    sv.p_drop = adrop.p > 0.f ? c.act((int64_t)B * cf.heads * L * Tkp) : nullptr;
+  }
   sv.ctx = c.act((int64_t)M * d);
   RUN(layernorm_fwd(x_in, F32, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), cf.ln_eps, sv.h, c.adt, nullptr, sv.mean, sv.rstd,
                     M, d, 0, c.st));
@@ -400,7 +424,7 @@ static int cross_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_i
   B200ST_TRY(linear_fwd(c, sv.h, d, M, d, d, pre + ".q.kernel", pre + ".q.bias", e0, sv.qkv, c.adt, d));
   B200ST_TRY(linear_fwd(c, mem, d, Mk, d, 2 * d, pre + ".kv.kernel", pre + ".kv.bias", e0, sv.kv, c.adt, 2 * d));
   View q{sv.qkv, d}, k{sv.kv, 2 * d}, v{c.act_off(sv.kv, d), 2 * d};
-  B200ST_TRY(attention_fwd(c, sv.dims, q, k, v, mem_bias, 0, adrop, sc.S, sv.p_pre, sv.p_drop, sv.ctx));
+  B200ST_TRY(attention_fwd(c, sv.dims, q, k, v, mem_bias, 0, adrop, sc.S, sv.p_pre, sv.p_drop, sv.ctx, sv.lse));
   GemmEpilogue e1 = gemm_defaults().epi;
   e1.drop = c.drop(cf.postprocess_dropout, sv.s_post);
   e1.residual = x_in; e1.res_ld = d;
@@ -419,7 +443,7 @@ static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_
   View q{sv.qkv, d}, k{sv.kv, 2 * d}, v{c.act_off(sv.kv, d), 2 * d};
   View dq{sc.dqkv, d}, dk{sc.dkv, 2 * d}, dv{c.act_off(sc.dkv, d), 2 * d};
   B200ST_TRY(attention_bwd(c, sv.dims, q, k, v, sv.p_pre, sv.p_drop, c.drop(cf.attention_dropout, sv.s_attn), sc.dctx, sc.S, sc.dS,
-                           dq, dk, dv));
+                           dq, dk, dv, sv.ctx, sv.lse, sv.bias, 0, sc.dq32));
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, d, M, d, d, pre + ".q.kernel", pre + ".q.bias"));
   B200ST_TRY(linear_dgrad(c, sc.dqkv, d, M, d, d, pre + ".q.kernel", e0, sc.dh, F32, d));
   RUN(layernorm_bwd(sc.dh, F32, sv.x_in, F32, sv.mean, sv.rstd, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), dx_out, dx_in, F32,
@@ -490,6 +514,7 @@ static void alloc_scratch(Ctx& c, Scratch& sc, int B, int Tq_max, int Tk_max, in
     sc.dkv = c.act((int64_t)Mk_max * 2 * cf.d);
     sc.dF1 = c.act((int64_t)Mq_max * cf.ffn);
     sc.dh = c.f32((int64_t)Mq_max * cf.d);
+    sc.dq32 = c.f32((int64_t)Mq_max * cf.d);
   }
 }
 
@@ -859,13 +884,14 @@ int mha_api_body(Ctx& c, const float* query, const float* memory, const float* b
   float* S = c.f32((int64_t)B * cf.heads * Tq * round8(Tk));
   void* p_pre = c.act((int64_t)B * cf.heads * Tq * round8(Tk));
   void* ctx = c.act(Mq * u);
+  float* lse = c.f32((int64_t)B * cf.heads * Tq);
   GemmEpilogue e0 = gemm_defaults().epi;
   AttnDims dims{B, cf.heads, Tq, Tk, u};
   if (cf.mha_self) {
     void* qkv = c.act(Mq * 3 * u);
     B200ST_TRY(linear_fwd(c, qin, cf.mha_din, (int)Mq, cf.mha_din, 3 * u, "att.qkv.kernel", "att.qkv.bias", e0, qkv, c.adt, 3 * u));
     View q{qkv, 3 * u}, k{c.act_off(qkv, u), 3 * u}, v{c.act_off(qkv, 2 * u), 3 * u};
-    B200ST_TRY(attention_fwd(c, dims, q, k, v, bias, 0, no_dropout(), S, p_pre, nullptr, ctx));
+    B200ST_TRY(attention_fwd(c, dims, q, k, v, bias, 0, no_dropout(), S, p_pre, nullptr, ctx, lse));
   } else {
     void* min = c.act(Mk * cf.mha_dmem);
     RUN(cast_dropout(memory, min, c.adt, Mk * cf.mha_dmem, no_dropout(), c.st));
@@ -874,7 +900,7 @@ int mha_api_body(Ctx& c, const float* query, const float* memory, const float* b
     B200ST_TRY(linear_fwd(c, qin, cf.mha_din, (int)Mq, cf.mha_din, u, "att.q.kernel", "att.q.bias", e0, qb, c.adt, u));
     B200ST_TRY(linear_fwd(c, min, cf.mha_dmem, (int)Mk, cf.mha_dmem, 2 * u, "att.kv.kernel", "att.kv.bias", e0, kv, c.adt, 2 * u));
     View q{qb, u}, k{kv, 2 * u}, v{c.act_off(kv, u), 2 * u};
-    B200ST_TRY(attention_fwd(c, dims, q, k, v, bias, 0, no_dropout(), S, p_pre, nullptr, ctx));
+    B200ST_TRY(attention_fwd(c, dims, q, k, v, bias, 0, no_dropout(), S, p_pre, nullptr, ctx, lse));
   }
   return linear_fwd(c, ctx, u, (int)Mq, u, cf.mha_dout, "att.out.kernel", "att.out.bias", e0, out, F32, cf.mha_dout);
 }

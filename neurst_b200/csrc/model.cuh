@@ -23,6 +23,7 @@ struct Config {
   // MODEL_MHA only
   int mha_self, mha_din, mha_dmem, mha_dout;
   int with_cross_attention;   // decoder stack: 1 (default)
+  int disable_fused_attention; // tests: use the materialised (GEMM + softmax) attention path in bf16 mode
 };
 
 struct ParamInfo {

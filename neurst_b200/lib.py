@@ -156,7 +156,7 @@ class Config(C.Structure):
                 ("postprocess_dropout", C.c_float), ("label_smoothing", C.c_float),
                 ("share_src_trg_embedding", C.c_int32),
                 ("mha_self", C.c_int32), ("mha_din", C.c_int32), ("mha_dmem", C.c_int32), ("mha_dout", C.c_int32),
-                ("with_cross_attention", C.c_int32)]
+                ("with_cross_attention", C.c_int32), ("disable_fused_attention", C.c_int32)]
 
 
 class Buffers(C.Structure):

@@ -119,3 +119,51 @@ def test_cuda_graph_step_matches_eager():
     assert U.rel_err(rt.grads, g_eager) < 1e-4
     rt.grads.zero_()
     assert abs(float(step(batch, 78)["loss"]) - loss_eager) > 1e-7
+
+
+FUSED_CFG = dict(model="speech", d=128, heads=2, enc_layers=2, dec_layers=2, ffn=128, channels=64, feat=80, in_channels=1, vocab=96)
+
+
+@pytest.mark.parametrize("T,dropout", [(600, 0.0), (600, 0.1), (1100, 0.1)])
+def test_fused_attention_path_vs_oracle(T, dropout):
+    """head dim 64 => the fused tcgen05 flash-attention kernels (forward + backward): multiple q tiles / kv blocks,
+    ragged key lengths (additive -1e9 key bias), causal decoder self-attention, cross-attention, Philox dropout."""
+    cfg = FUSED_CFG
+    P = R.init_params(cfg, seed=11, random_bias=True)
+    B, Lq = 2, 9
+    batch = U.synthetic_speech_batch(cfg, B, T, Lq, seed=5)
+    rt = U.speech_runtime(cfg, "bf16", dropout=dropout, label_smoothing=0.1)
+    rt.load_parameters(P)
+    seed = 99
+    cb = U.to_cuda(batch)
+    cb.update(training=dropout > 0, seed=seed, want_logits=True)
+    rt.ensure_grads().zero_()
+    out = rt.run(cb, backward=True)
+    T2 = R.length_after_conv(T)
+    masks = U.dropout_masks(rt, cfg, B, T2, Lq, dropout, seed) if dropout > 0 else R.NO_DROPOUT
+    logits, loss, grads = U.oracle_loss_and_grads(P, cfg, batch, 0.1, masks)
+    assert float((out["logits"].cpu().double() - logits).abs().max()) < 6e-2
+    assert abs(float(out["loss"]) - float(loss)) < 3e-2
+    worst = max((U.rel_err(rt.grad_view(k), g), k) for k, g in grads.items())
+    assert worst[0] < 1e-1, worst
+
+
+def test_fused_attention_matches_materialised_path():
+    from neurst_b200 import lib as L
+    from neurst_b200.runtime import Runtime, make_config
+    cfg = FUSED_CFG
+    P = R.init_params(cfg, seed=11, random_bias=True)
+    batch = U.to_cuda(U.synthetic_speech_batch(cfg, 2, 600, 9, seed=5))
+    res = []
+    for disable in (False, True):
+        c = make_config(L.MODEL_SPEECH, cfg["d"], cfg["heads"], cfg["ffn"], 2, 2, cfg["vocab"], channels=cfg["channels"],
+                        precision="bf16", attention_dropout=0.1, ffn_dropout=0.1, postprocess_dropout=0.1, label_smoothing=0.1,
+                        disable_fused_attention=disable)
+        rt = Runtime(c)
+        rt.load_parameters(P)
+        rt.ensure_grads().zero_()
+        b = dict(batch); b.update(training=True, seed=5, want_logits=True)
+        out = rt.run(b, backward=True)
+        res.append((out["logits"].clone(), rt.grads.clone()))
+    assert float((res[0][0] - res[1][0]).abs().max()) < 3e-2
+    assert U.rel_err(res[0][1], res[1][1]) < 3e-2
