@@ -62,28 +62,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ==============================================================================================================
-// forward
+// forward: 320 threads = TMA warp + MMA warp + 8 softmax warps (2 per TMEM lane quadrant, each owning 64 of the 128
+// key columns of a block); ~84 KB smem and 256 TMEM columns so that two CTAs share an SM.
 // ==============================================================================================================
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(320, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;                          // 16 KB
-  const uint32_t sK = sQ + kTile16K;                 // 2 x 16 KB
-  const uint32_t sV = sK + 2 * kTile16K;             // 2 x 16 KB
-  const uint32_t sP = sV + 2 * kTile16K;             // 2 x 32 KB
-  const uint32_t bars = sP + 4 * kTile16K;
-  const uint32_t q_full = bars;
-  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bars + 8u * (3 + s); };
-  auto s_full = [&](int s) { return bars + 8u * (5 + s); };
-  auto s_empty = [&](int s) { return bars + 8u * (7 + s); };
-  auto p_full = [&](int s) { return bars + 8u * (9 + s); };
-  auto p_empty = [&](int s) { return bars + 8u * (11 + s); };
-  const uint32_t o_ready = bars + 8u * 13;
-  const uint32_t tmem_slot = bars + 8u * 14;
+  const uint32_t sK = sQ + kTile16K;                 // 16 KB
+  const uint32_t sV = sK + kTile16K;                 // 16 KB
+  const uint32_t sP = sV + kTile16K;                 // 32 KB
+  const uint32_t sX = sP + 2 * kTile16K;             // exchange: max [2][2][128] + sum [2][128] floats = 3 KB
+  const uint32_t bars = sX + 3072;
+  const uint32_t q_full = bars, kv_full = bars + 8, kv_empty = bars + 16, s_full = bars + 24, s_empty = bars + 32,
+                 p_full = bars + 40, p_empty = bars + 48, o_ready = bars + 56, tmem_slot = bars + 64;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+  float* xch = reinterpret_cast<float*>(smem_raw + (sX - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -92,32 +90,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
     ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(kv_full(s), 1); ptx::mbar_init(kv_empty(s), 1);
-      ptx::mbar_init(s_full(s), 1); ptx::mbar_init(s_empty(s), 4);
-      ptx::mbar_init(p_full(s), 4); ptx::mbar_init(p_empty(s), 1);
-    }
+    ptx::mbar_init(kv_full, 1); ptx::mbar_init(kv_empty, 1);
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(s_empty, 8);
+    ptx::mbar_init(p_full, 8); ptx::mbar_init(p_empty, 1);
     ptx::mbar_init(o_ready, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) { ptx::tmem_alloc_n<512>(tmem_slot); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc_n<256>(tmem_slot); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tS = tmem;            // 2 x 128 columns
-  const uint32_t tO = tmem + 256;      // 64 columns
+  const uint32_t tS = tmem;            // 128 columns
+  const uint32_t tO = tmem + 128;      // 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(q_full, kTile16K);
       ptx::tma_load_4d(sQ, &tmQ, q_full, 0, qt * BQ, h, b);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        ptx::mbar_wait(kv_empty(st), (((uint32_t)j >> 1) & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(kv_full(st), 2 * kTile16K);
-        ptx::tma_load_4d(sK + st * kTile16K, &tmK, kv_full(st), 0, j * BKV, h, b);
-        ptx::tma_load_4d(sV + st * kTile16K, &tmV, kv_full(st), 0, j * BKV, h, b);
+        ptx::mbar_wait(kv_empty, ((uint32_t)j & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(kv_full, 2 * kTile16K);
+        ptx::tma_load_4d(sK, &tmK, kv_full, 0, j * BKV, h, b);
+        ptx::tma_load_4d(sV, &tmV, kv_full, 0, j * BKV, h, b);
       }
     }
   } else if (warp == 1) {
@@ -125,40 +120,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t idesc_s = ptx::make_idesc_bf16(BKV, 0, 0);    // S[128 x 128] = Q K^T, both K-major
       const uint32_t idesc_o = ptx::make_idesc_bf16(DH, 0, 1);     // O[128 x 64] += P V, V as MN-major B
       ptx::mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        const uint32_t ph = ((uint32_t)j >> 1) & 1u;
-        ptx::mbar_wait(kv_full(st), ph);
-        ptx::mbar_wait(s_empty(st), ph ^ 1u);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) {
-          const uint64_t da = ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024);
-          const uint64_t db = ptx::make_smem_desc_sw128(sK + st * kTile16K + k * 32, 16, 1024);
-          ptx::mma_f16_ss(tS + st * BKV, da, db, idesc_s, k > 0 ? 1u : 0u);
-        }
-        ptx::mma_commit(s_full(st));
-      };
-      issue_s(0);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        if (j + 1 < nblk) issue_s(j + 1);
-        ptx::mbar_wait(p_full(st), ((uint32_t)j >> 1) & 1u);
+        const uint32_t ph = (uint32_t)j & 1u;
+        ptx::mbar_wait(kv_full, ph);
+        ptx::mbar_wait(s_empty, ph ^ 1u);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t da = ptx::make_smem_desc_sw128(sP + st * 2 * kTile16K + (k >> 2) * kTile16K + (k & 3) * 32, 16, 1024);
-          const uint64_t db = ptx::make_smem_desc_sw128(sV + st * kTile16K + k * 2048, 8192, 1024);
-          ptx::mma_f16_ss(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        }
-        ptx::mma_commit(kv_empty(st));
-        ptx::mma_commit(p_empty(st));
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::mma_f16_ss(tS, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                          idesc_s, k > 0 ? 1u : 0u);
+        ptx::mma_commit(s_full);
+        ptx::mbar_wait(p_full, ph);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          ptx::mma_f16_ss(tO, ptx::make_smem_desc_sw128(sP + (k >> 2) * kTile16K + (k & 3) * 32, 16, 1024),
+                          ptx::make_smem_desc_sw128(sV + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        ptx::mma_commit(kv_empty);
+        ptx::mma_commit(p_empty);
         ptx::mma_commit(o_ready);
       }
     }
   } else {
-    // ---------------- softmax warps: one thread per query row ----------------
+    // ---------------- softmax warps: thread = (query row, half of the key columns) ----------------
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int q = qt * BQ + row;
     const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
@@ -166,19 +152,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t thresh = dropout_thresh16(p.drop.p);
     const uint64_t seed = p.drop.p > 0.f ? dropout_seed(p.drop) : 0ull;
-    float m = -INFINITY, l = 0.f;      // running max (log2 domain) and sum
+    float m = -INFINITY, l = 0.f;      // running row max (log2 domain, shared by both halves) and this half's partial sum
     for (int j = 0; j < nblk; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = ((uint32_t)j >> 1) & 1u;
-      ptx::mbar_wait(s_full(st), ph);
+      const uint32_t ph = (uint32_t)j & 1u;
+      ptx::mbar_wait(s_full, ph);
       ptx::tc_fence_after();
-      // pass 1: block maximum
+      // pass 1: maximum over this half's 64 columns, then exchange with the partner warp
       float bmax = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         uint32_t r[32];
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tS + lane_addr + st * BKV + c0, r);
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -186,33 +171,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (k < p.Tk) bmax = fmaxf(bmax, logit(p, __uint_as_float(r[i]), bias_row, k, q) * kLog2e);
         }
       }
+      xch[(ph * 2 + half) * 128 + row] = bmax;
+      softmax_bar();
+      bmax = fmaxf(bmax, xch[(ph * 2 + (half ^ 1)) * 128 + row]);
       const float m_new = fmaxf(m, bmax);
       const float corr = exp2f(m - m_new);           // 0 on the first block (m = -inf)
-      // rescale the running output once the previous PV product has landed
+      // rescale this half's 32 output columns once the previous PV product has landed
       if (j > 0) {
-        ptx::mbar_wait(o_ready, (uint32_t)(j - 1) & 1u);
+        ptx::mbar_wait(o_ready, ph ^ 1u);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t r[32];
-          __syncwarp();
-          ptx::tmem_ld_32x32b_x32(tO + lane_addr + c0, r);
-          ptx::tmem_ld_wait();
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tO + lane_addr + half * 32, r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
-          ptx::tmem_st_32x32b_x32(tO + lane_addr + c0, r);
-        }
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+        ptx::tmem_st_32x32b_x32(tO + lane_addr + half * 32, r);
         ptx::tmem_st_wait();
       }
       // pass 2: probabilities -> bf16 P tile in shared memory (A operand of the PV product)
-      ptx::mbar_wait(p_empty(st), ph ^ 1u);
+      ptx::mbar_wait(p_empty, ph ^ 1u);
       float bsum = 0.f;
-      const uint32_t p_base = sP + st * 2 * kTile16K;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         uint32_t r[32];
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tS + lane_addr + st * BKV + c0, r);
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -231,8 +215,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) pv[i] = ((keep >> i) & 1u) ? pv[i] * p.drop.scale : 0.f;
           }
-          st_shared_v4(p_base + swz_off(row, c0 + g8 * 8), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]),
-                       pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
+          st_shared_v4(sP + swz_off(row, c0 + g8 * 8), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                       pack_bf16(pv[6], pv[7]));
         }
       }
       l = l * corr + bsum;
@@ -240,18 +224,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::fence_proxy_async_smem();       // P (generic-proxy writes) -> visible to the tensor-core (async) proxy
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(s_empty(st)); ptx::mbar_arrive(p_full(st)); }
+      if (lane == 0) { ptx::mbar_arrive(s_empty); ptx::mbar_arrive(p_full); }
     }
     // ---- epilogue: O / l -> ctx, LSE ----
+    float* xsum = xch + 512;
+    xsum[half * 128 + row] = l;
+    softmax_bar();
+    l += xsum[(half ^ 1) * 128 + row];
     ptx::mbar_wait(o_ready, (uint32_t)(nblk - 1) & 1u);
     ptx::tc_fence_after();
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* dst = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH;
-#pragma unroll 1
-    for (int c0 = 0; c0 < DH; c0 += 32) {
+    __nv_bfloat16* dst = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH + half * 32;
+    {
       uint32_t r[32];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(tO + lane_addr + c0, r);
+      ptx::tmem_ld_32x32b_x32(tO + lane_addr + half * 32, r);
       ptx::tmem_ld_wait();
       if (q < p.Tq) {
 #pragma unroll
@@ -261,18 +248,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           pk.y = pack_bf16(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
           pk.z = pack_bf16(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
           pk.w = pack_bf16(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+          *reinterpret_cast<uint4*>(dst + i) = pk;
         }
       }
     }
-    if (q < p.Tq && p.lse) p.lse[row_g] = m * kLn2 + logf(l);
+    if (half == 0 && q < p.Tq && p.lse) p.lse[row_g] = m * kLn2 + logf(l);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
 }
-
 
 // ==============================================================================================================
 // backward: one CTA per (kv block, head, batch)
@@ -281,7 +267,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -311,8 +297,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV); ptx::prefetch_tensormap(&tmdO);
     ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(qdo_full(s), 1); ptx::mbar_init(qdo_empty(s), 1); }
-    ptx::mbar_init(sdp_full, 1); ptx::mbar_init(pds_full, 4);
-    ptx::mbar_init(dq_full, 1); ptx::mbar_init(dq_empty, 4);
+    ptx::mbar_init(sdp_full, 1); ptx::mbar_init(pds_full, 8);
+    ptx::mbar_init(dq_full, 1); ptx::mbar_init(dq_empty, 8);
     ptx::fence_mbar_init();
   }
   if (warp == 1) { ptx::tmem_alloc_n<512>(tmem_slot); ptx::tmem_relinquish(); }
@@ -381,7 +367,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
+    // 8 compute warps: thread = (row of the tile, half of the columns); no cross-warp reductions are needed in backward
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
@@ -412,7 +400,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_wait(sdp_full, (uint32_t)i & 1u);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         uint32_t rs[32], rp[32];
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
@@ -451,20 +439,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pds_full);
-      // ---- dQ tile -> fp32 reduction across kv blocks ----
+      // ---- dQ tile (this half's 32 columns) -> fp32 reduction across kv blocks ----
       ptx::mbar_wait(dq_full, (uint32_t)i & 1u);
       ptx::tc_fence_after();
-      float* dq_row = p.dq_acc + ((int64_t)b * p.Tq + q) * p.dq_ld + h * DH;
-#pragma unroll 1
-      for (int c0 = 0; c0 < DH; c0 += 32) {
+      float* dq_row = p.dq_acc + ((int64_t)b * p.Tq + q) * p.dq_ld + h * DH + half * 32;
+      {
         uint32_t r[32];
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tdQ + lane_addr + c0, r);
+        ptx::tmem_ld_32x32b_x32(tdQ + lane_addr + half * 32, r);
         ptx::tmem_ld_wait();
         if (qv) {
 #pragma unroll
           for (int t = 0; t < 32; t += 4)
-            red_add_v4(dq_row + c0 + t, __uint_as_float(r[t]) * p.alpha, __uint_as_float(r[t + 1]) * p.alpha,
+            red_add_v4(dq_row + t, __uint_as_float(r[t]) * p.alpha, __uint_as_float(r[t + 1]) * p.alpha,
                        __uint_as_float(r[t + 2]) * p.alpha, __uint_as_float(r[t + 3]) * p.alpha);
         }
       }
@@ -472,16 +459,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(dq_empty);
     }
-    // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them) ----
+    // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them); 32 columns per half ----
     const int kk = jb * BKV + row;
-    __nv_bfloat16* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH;
-    __nv_bfloat16* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH;
-#pragma unroll 1
-    for (int c0 = 0; c0 < DH; c0 += 32) {
+    __nv_bfloat16* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH + half * 32;
+    __nv_bfloat16* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH + half * 32;
+    {
       uint32_t rv[32], rk[32];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(tdV + lane_addr + c0, rv);
-      ptx::tmem_ld_32x32b_x32(tdK + lane_addr + c0, rk);
+      ptx::tmem_ld_32x32b_x32(tdV + lane_addr + half * 32, rv);
+      ptx::tmem_ld_32x32b_x32(tdK + lane_addr + half * 32, rk);
       ptx::tmem_ld_wait();
       if (kk < p.Tk) {
 #pragma unroll
@@ -495,8 +481,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           c.y = pack_bf16(__uint_as_float(rk[t + 2]) * p.alpha, __uint_as_float(rk[t + 3]) * p.alpha);
           c.z = pack_bf16(__uint_as_float(rk[t + 4]) * p.alpha, __uint_as_float(rk[t + 5]) * p.alpha);
           c.w = pack_bf16(__uint_as_float(rk[t + 6]) * p.alpha, __uint_as_float(rk[t + 7]) * p.alpha);
-          *reinterpret_cast<uint4*>(dv_row + c0 + t) = a;
-          *reinterpret_cast<uint4*>(dk_row + c0 + t) = c;
+          *reinterpret_cast<uint4*>(dv_row + t) = a;
+          *reinterpret_cast<uint4*>(dk_row + t) = c;
         }
       }
     }
@@ -523,7 +509,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, 
   }
 }
 
-constexpr size_t kFwdSmem = 1024 + (size_t)(1 + 2 + 2 + 4) * kTile16K + 8 * 16 + 64;
+constexpr size_t kFwdSmem = 1024 + (size_t)(1 + 1 + 1 + 2) * kTile16K + 3072 + 8 * 10 + 64;
 
 }  // namespace
 
@@ -549,7 +535,7 @@ int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
     attr = true;
   }
   dim3 grid((Tq + BQ - 1) / BQ, H, B);
-  attn_fwd_kernel<<<grid, 192, kFwdSmem, s>>>(tq, tk, tv, p);
+  attn_fwd_kernel<<<grid, 320, kFwdSmem, s>>>(tq, tk, tv, p);
   tc_count_launch();
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -587,7 +573,7 @@ int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
   const int64_t rows = (int64_t)B * Tq;
   B200ST_CUDA(cudaMemsetAsync(dq_scratch, 0, sizeof(float) * (size_t)rows * H * DH, s));
   dim3 grid((Tk + BKV - 1) / BKV, H, B);
-  attn_bwd_kernel<<<grid, 192, kBwdSmem, s>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<<<grid, 320, kBwdSmem, s>>>(tq, tk, tv, tdo, p);
   B200ST_LAUNCH_CHECK();
   const int64_t n8 = rows * (H * DH / 8);
   int64_t g = (n8 + 255) / 256;

@@ -49,6 +49,14 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* ds
 template <bool VEC> __device__ __forceinline__ int chan(int lane, int i) {
   return VEC ? (8 * lane + 256 * (i >> 3) + (i & 7)) : (lane + 32 * i);
 }
+// Shared-memory slot of channel c within a per-channel table: permuted so that the 32 lanes of a warp reading
+// "their i-th channel" hit 32 consecutive banks (the natural order would be an 8-way bank conflict for VEC).
+template <bool VEC> __device__ __forceinline__ int slot_of_channel(int c) {
+  return VEC ? ((c & ~255) + ((c & 7) << 5) + ((c & 255) >> 3)) : c;
+}
+template <bool VEC> __device__ __forceinline__ int slot(int lane, int i) {
+  return VEC ? (256 * (i >> 3) + 32 * (i & 7) + lane) : (lane + 32 * i);
+}
 
 // Loads / stores the CPL channels a lane owns at row pointer p (C channels per row).
 template <typename T, bool VEC, int CPL>
@@ -96,31 +104,33 @@ template <bool VEC, int CPL, bool CIN1>
 struct ConvTaps {
   const float* sw;      // smem [9*Cin][C]
   const float* sb;      // smem [C]
+  int cp;               // padded channel count of one table row
   __device__ __forceinline__ void init(float* smem, const float* __restrict__ w, const float* __restrict__ bias, int Cin, int C) {
-    const int nw = 9 * Cin * C;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) smem[i] = w[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) smem[nw + i] = bias[i];
-    sw = smem; sb = smem + nw;
+    const int Cp = VEC ? ((C + 255) & ~255) : C;       // padded row so that permuted slots stay in range
+    const int nw = 9 * Cin * Cp;
+    for (int i = threadIdx.x; i < 9 * Cin * C; i += blockDim.x) smem[(i / C) * Cp + slot_of_channel<VEC>(i % C)] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) smem[nw + slot_of_channel<VEC>(i)] = bias[i];
+    sw = smem; sb = smem + nw; cp = Cp;
     __syncthreads();
   }
   // xv: the 9*Cin input taps of this position (zero outside), in (kh,kw,ci) order
   __device__ __forceinline__ void apply(const float* xv, int lane, int Cin, int C, float (&z)[CPL]) const {
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); z[i] = c < C ? sb[c] : 0.f; }
+    for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); z[i] = c < C ? sb[slot<VEC>(lane, i)] : 0.f; }
     if (CIN1) {
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) {
         const float x = xv[tp];
-        const float* wr = sw + tp * C;
+        const float* wr = sw + tp * cp;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, wr[c], z[i]); }
+        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, wr[slot<VEC>(lane, i)], z[i]); }
       }
     } else {
       for (int k = 0; k < 9 * Cin; ++k) {
         const float x = xv[k];
-        const float* wr = sw + k * C;
+        const float* wr = sw + k * cp;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, wr[c], z[i]); }
+        for (int i = 0; i < CPL; ++i) { const int c = chan<VEC>(lane, i); if (c < C) z[i] = fmaf(x, wr[slot<VEC>(lane, i)], z[i]); }
       }
     }
   }
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 2 : 1)) conv1_bwd_fused_kerne
     T* __restrict__ col1, int K1p, float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn,
     int F, int Cin, int C, int T1, int F1, int T2, int F2, int use_ln) {
   extern __shared__ float conv_smem[];   // filter | bias | [3][C] block partials: db | dgamma | dbeta
-  float* sacc = conv_smem + (9 * (CIN1 ? 1 : Cin) + 1) * C;
+  float* sacc = conv_smem + (9 * (CIN1 ? 1 : Cin) + 1) * (VEC ? ((C + 255) & ~255) : C);
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
   const int lane = threadIdx.x & 31;
   ConvTaps<VEC, CPL, CIN1> taps;
@@ -338,7 +348,7 @@ int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const fl
   if (npos == 0) return 0;
   const int grid = pick_grid(npos, 8 * 4, 148 * 12);
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0);
-  const size_t smem = (size_t)(9 * Cin + 1) * C * sizeof(float);
+  const size_t smem = (size_t)(9 * Cin + 1) * ((C + 255) & ~255) * sizeof(float);
   B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
 #define FWD(VEC, CPL, CIN1)                                                                                             \
   DISPATCH_DTYPE(y_dtype, TT, (conv1_fwd_kernel<TT, VEC, CPL, CIN1><<<grid, 256, smem, s>>>(src, w, b, gamma, beta, eps, (TT*)y1, \
@@ -362,7 +372,7 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
   const int64_t npos = (int64_t)B * T1 * F1;
   if (npos == 0) return 0;
   const int grid = pick_grid(npos, 8 * 4, 148 * 8);
-  const size_t smem = (size_t)(9 * Cin + 1 + 3) * C * sizeof(float);
+  const size_t smem = (size_t)(9 * Cin + 1 + 3) * ((C + 255) & ~255) * sizeof(float);
   B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dz1) & 15) == 0);

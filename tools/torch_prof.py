@@ -17,7 +17,8 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 tot = 0.0
 for e in prof.events():
     if e.device_type is not None and "cuda" in str(e.device_type).lower():
-        name = re.sub(r"\(.*", "", e.name)
+        name = e.name.replace("(anonymous namespace)::", "")
+        name = re.sub(r"\(.*", "", name)
         name = re.sub(r"^void ", "", name)
         agg[name[:80]][0] += 1
         agg[name[:80]][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
