@@ -151,7 +151,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t thresh = dropout_thresh16(p.drop.p);
-    const uint64_t seed = p.drop.p > 0.f ? dropout_seed(p.drop) : 0ull;
     float m = -INFINITY, l = 0.f;      // running row max (log2 domain, shared by both halves) and this half's partial sum
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
@@ -211,7 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pv[i] = pr;
           }
           if (p.drop.p > 0.f) {
-            const uint32_t keep = dropout_keep8(seed, p.drop.stream, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
+            const uint32_t keep = drop_keep8(p.drop, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) pv[i] = ((keep >> i) & 1u) ? pv[i] * p.drop.scale : 0.f;
           }
@@ -374,7 +373,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
     const uint32_t thresh = dropout_thresh16(p.drop.p);
-    const uint64_t seed = p.drop.p > 0.f ? dropout_seed(p.drop) : 0ull;
     for (int i = 0; i < nq; ++i) {
       const int q = i * BQ + row;
       const bool qv = q < p.Tq;
@@ -410,7 +408,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int g8 = 0; g8 < 4; ++g8) {
           const int k0 = jb * BKV + c0 + g8 * 8;
           uint32_t keep = 0xffu;
-          if (p.drop.p > 0.f) keep = dropout_keep8(seed, p.drop.stream, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
+          if (p.drop.p > 0.f) keep = drop_keep8(p.drop, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
           float pd[8], ds[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {

@@ -69,7 +69,7 @@ static int convert_gemm(const b200st_gemm_args* a, GemmArgs& g) {
   g.epi.mask_ld = a->mask_ld; g.epi.mask_sb1 = a->mask_sb1; g.epi.mask_sb2 = a->mask_sb2;
   if (a->dropout_p > 0.f) {
     B200ST_CHECK(a->dropout_p < 1.f, "dropout_p must be < 1");
-    g.epi.drop = DropoutSpec{a->dropout_p, 1.f / (1.f - a->dropout_p), a->dropout_seed, a->dropout_stream, nullptr};
+    g.epi.drop = DropoutSpec{a->dropout_p, 1.f / (1.f - a->dropout_p), a->dropout_seed, a->dropout_stream, nullptr, nullptr};
   }
   g.epi.residual = a->residual; g.epi.res_ld = a->res_ld; g.epi.res_sb1 = a->res_sb1; g.epi.res_sb2 = a->res_sb2;
   g.epi.accumulate = a->accumulate;

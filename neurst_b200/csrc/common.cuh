@@ -114,9 +114,17 @@ struct DropoutSpec {
   uint64_t seed;
   uint64_t stream;  // unique id of the dropout site (layer, op)
   const uint64_t* seed_ptr;   // optional device address of the seed (CUDA-graph replay with a fresh seed per step)
+  const uint8_t* bits;        // optional precomputed keep-bits (byte g = dropout_keep8 of group g); same values as Philox
 };
-__host__ __device__ __forceinline__ DropoutSpec no_dropout() { return DropoutSpec{0.f, 1.f, 0, 0, nullptr}; }
+__host__ __device__ __forceinline__ DropoutSpec no_dropout() { return DropoutSpec{0.f, 1.f, 0, 0, nullptr, nullptr}; }
 __device__ __forceinline__ uint64_t dropout_seed(const DropoutSpec& d) { return d.seed_ptr ? *d.seed_ptr : d.seed; }
+// keep-bits of group g (elements [8g, 8g+8)): from the precomputed bitmap when present, else regenerated
+__device__ __forceinline__ uint32_t drop_keep8(const DropoutSpec& d, uint64_t group, uint32_t thresh) {
+  return d.bits ? (uint32_t)__ldg(d.bits + group) : dropout_keep8(dropout_seed(d), d.stream, group, thresh);
+}
+__device__ __forceinline__ bool drop_keep1(const DropoutSpec& d, uint64_t e) {
+  return (drop_keep8(d, e >> 3, dropout_thresh16(d.p)) >> (e & 7)) & 1u;
+}
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

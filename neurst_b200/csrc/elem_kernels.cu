@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
         for (int j = 0; j < 8; ++j) v[st][j] *= inv;
         store8<T>(P_pre + row * ldP + k0, v[st]);
         if (drop.p > 0.f) {
-          const uint32_t keep = dropout_keep8(dropout_seed(drop), drop.stream, (uint64_t)(row * ldP + k0) >> 3, thresh);
+          const uint32_t keep = drop_keep8(drop, (uint64_t)(row * ldP + k0) >> 3, thresh);
           float w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
         load8<float>(dP + row * ldS + k0, d[st]);
         load8<T>(P_pre + row * ldP + k0, pr[st]);
         uint32_t keep = 0xffu;
-        if (drop.p > 0.f) keep = dropout_keep8(dropout_seed(drop), drop.stream, (uint64_t)(row * ldP + k0) >> 3, thresh);
+        if (drop.p > 0.f) keep = drop_keep8(drop, (uint64_t)(row * ldP + k0) >> 3, thresh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (k0 + j >= Tk) { d[st][j] = 0.f; pr[st][j] = 0.f; }
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(256) cast_dropout_kernel(const float* __restri
   const int64_t ngroups = (n + 7) / 8;
   const bool vec = (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t keep = drop.p > 0.f ? dropout_keep8(dropout_seed(drop), drop.stream, (uint64_t)g, thresh) : 0xffu;
+    const uint32_t keep = drop.p > 0.f ? drop_keep8(drop, (uint64_t)g, thresh) : 0xffu;
     float v[8];
     if (vec) {
       load8<float>(x + g * 8, v);
@@ -609,7 +609,7 @@ __global__ void posenc_fwd_kernel(const float* __restrict__ v, float* __restrict
     const int c = (int)(i % d);
     const int t = (int)((i / d) % T);
     float val = v[i] * scale + sinusoid(t + t0, c, d);
-    if (drop.p > 0.f) val = dropout_keep(dropout_seed(drop), drop.stream, (uint64_t)i, drop.p) ? val * drop.scale : 0.f;
+    if (drop.p > 0.f) val = drop_keep1(drop, (uint64_t)i) ? val * drop.scale : 0.f;
     x[i] = val;
   }
 }
@@ -626,7 +626,7 @@ template <typename T>
 __global__ void posenc_bwd_kernel(const float* __restrict__ dx, T* __restrict__ dv, int64_t n, float scale, DropoutSpec drop) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float g = dx[i];
-    if (drop.p > 0.f) g = dropout_keep(dropout_seed(drop), drop.stream, (uint64_t)i, drop.p) ? g * drop.scale : 0.f;
+    if (drop.p > 0.f) g = drop_keep1(drop, (uint64_t)i) ? g * drop.scale : 0.f;
     dv[i] = from_f32<T>(g * scale);
   }
 }
@@ -648,7 +648,7 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const float* _
     int64_t id = ids[bl];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
     float val = E[id * d + c] * scale + sinusoid(l + t0, c, d);
-    if (drop.p > 0.f) val = dropout_keep(dropout_seed(drop), drop.stream, (uint64_t)i, drop.p) ? val * drop.scale : 0.f;
+    if (drop.p > 0.f) val = drop_keep1(drop, (uint64_t)i) ? val * drop.scale : 0.f;
     x[i] = val;
   }
 }
@@ -670,7 +670,7 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const float* _
     int64_t id = ids[bl];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
     float g = dx[i];
-    if (drop.p > 0.f) g = dropout_keep(dropout_seed(drop), drop.stream, (uint64_t)i, drop.p) ? g * drop.scale : 0.f;
+    if (drop.p > 0.f) g = drop_keep1(drop, (uint64_t)i) ? g * drop.scale : 0.f;
     atomicAdd(&dE[id * d + c], g * scale);
   }
 }
@@ -821,6 +821,20 @@ int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int
               float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s) {
   if (n == 0) return 0;
   adam_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void dropout_bits_kernel(DropoutSpec drop, int64_t ngroups, uint8_t* __restrict__ out) {
+  const uint32_t thresh = dropout_thresh16(drop.p);
+  const uint64_t seed = dropout_seed(drop);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x)
+    out[g] = (uint8_t)dropout_keep8(seed, drop.stream, (uint64_t)g, thresh);
+}
+int dropout_bits(DropoutSpec drop, int64_t n_elems, uint8_t* out, cudaStream_t s) {
+  const int64_t ng = (n_elems + 7) / 8;
+  if (ng == 0) return 0;
+  dropout_bits_kernel<<<grid_for(ng, 256), 256, 0, s>>>(drop, ng, out);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

@@ -62,7 +62,7 @@ __device__ __forceinline__ float gemm_epilogue_value(const GemmEpilogue& ep, flo
     float s = load_as_f32(ep.mask_src, ep.mask_dtype, boff_mask + (int64_t)m * ep.mask_ld + n);
     v = s > 0.f ? v : 0.f;
   }
-  if (ep.drop.p > 0.f) v = dropout_keep(dropout_seed(ep.drop), ep.drop.stream, e_idx, ep.drop.p) ? v * ep.drop.scale : 0.f;
+  if (ep.drop.p > 0.f) v = drop_keep1(ep.drop, e_idx) ? v * ep.drop.scale : 0.f;
   if (ep.residual) v += __ldg(ep.residual + boff_res + (int64_t)m * ep.res_ld + n);
   return v;
 }

@@ -58,6 +58,8 @@ int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_len
 // Keras Adam (epsilon-hat form) over a flat arena; optionally refreshes the bf16 shadow and zeroes g.
 int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
               float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s);
+// out[g] = keep-bits of elements [8g, 8g+8) of the dropout site (identical to the on-the-fly Philox decisions)
+int dropout_bits(DropoutSpec drop, int64_t n_elems, uint8_t* out, cudaStream_t s);
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s);
 int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 

@@ -152,9 +152,23 @@ struct Ctx {
   size_t esz() const { return adt == BF16 ? 2 : 4; }
   void* act(int64_t n) { return ar.take((size_t)n * esz()); }
   float* f32(int64_t n) { return reinterpret_cast<float*>(ar.take((size_t)n * 4)); }
-  DropoutSpec drop(float p, uint64_t stream) const {
+  std::unordered_map<uint64_t, DropoutSpec> drop_memo;
+  bool launch_failed = false;
+  // Dropout site `stream`.  The first (forward) use passes the element count: the keep-bits of the whole site are then
+  // generated once into the workspace (one Philox call per 8 elements, full-occupancy kernel) and every consumer —
+  // GEMM epilogues, fused attention, the backward pass — just reads bits.  Later uses return the memoised spec.
+  DropoutSpec drop(float p, uint64_t stream, int64_t n_elems = 0) {
     if (!training || p <= 0.f) return no_dropout();
-    return DropoutSpec{p, 1.f / (1.f - p), seed, stream, seed_dev};
+    auto it = drop_memo.find(stream);
+    if (it != drop_memo.end()) return it->second;
+    DropoutSpec d{p, 1.f / (1.f - p), seed, stream, seed_dev, nullptr};
+    if (n_elems > 0) {
+      uint8_t* bits = reinterpret_cast<uint8_t*>(ar.take((size_t)((n_elems + 7) / 8 + 4)));
+      if (!dry && dropout_bits(d, n_elems, bits, st) != 0) launch_failed = true;
+      d.bits = bits;
+      drop_memo[stream] = d;
+    }
+    return d;
   }
   const ParamInfo* info(const std::string& n) const {
     const int i = m.find(n);
@@ -359,7 +373,7 @@ static int self_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_in
   sv.s_attn = dropout_stream_id(pre + ".attn_drop"); sv.s_post = dropout_stream_id(pre + ".post_drop");
   sv.h = c.act((int64_t)M * d); sv.mean = c.f32(M); sv.rstd = c.f32(M);
   sv.qkv = c.act((int64_t)M * 3 * d);
-  const DropoutSpec adrop = c.drop(cf.attention_dropout, sv.s_attn);
+  const DropoutSpec adrop = c.drop(cf.attention_dropout, sv.s_attn, (int64_t)B * cf.heads * T * Tkp);
   if (use_fused_attention(c, sv.dims)) {
     sv.lse = c.f32((int64_t)B * cf.heads * T);
   } else {
@@ -374,7 +388,7 @@ static int self_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_in
   View q{sv.qkv, 3 * d}, k{c.act_off(sv.qkv, d), 3 * d}, v{c.act_off(sv.qkv, 2 * d), 3 * d};
   B200ST_TRY(attention_fwd(c, sv.dims, q, k, v, bias, causal, adrop, sc.S, sv.p_pre, sv.p_drop, sv.ctx, sv.lse));
   GemmEpilogue e1 = gemm_defaults().epi;
-  e1.drop = c.drop(cf.postprocess_dropout, sv.s_post);
+  e1.drop = c.drop(cf.postprocess_dropout, sv.s_post, (int64_t)M * d);
   e1.residual = x_in; e1.res_ld = d;
   B200ST_TRY(linear_fwd(c, sv.ctx, d, M, d, d, pre + ".out.kernel", pre + ".out.bias", e1, x_out, F32, d));
   return 0;
@@ -410,7 +424,7 @@ static int cross_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_i
   sv.h = c.act((int64_t)M * d); sv.mean = c.f32(M); sv.rstd = c.f32(M);
   sv.qkv = c.act((int64_t)M * d);
   sv.kv = c.act((int64_t)Mk * 2 * d);
-  const DropoutSpec adrop = c.drop(cf.attention_dropout, sv.s_attn);
+  const DropoutSpec adrop = c.drop(cf.attention_dropout, sv.s_attn, (int64_t)B * cf.heads * L * Tkp);
   if (use_fused_attention(c, sv.dims)) {
     sv.lse = c.f32((int64_t)B * cf.heads * L);
   } else {
@@ -426,7 +440,7 @@ static int cross_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_i
   View q{sv.qkv, d}, k{sv.kv, 2 * d}, v{c.act_off(sv.kv, d), 2 * d};
   B200ST_TRY(attention_fwd(c, sv.dims, q, k, v, mem_bias, 0, adrop, sc.S, sv.p_pre, sv.p_drop, sv.ctx, sv.lse));
   GemmEpilogue e1 = gemm_defaults().epi;
-  e1.drop = c.drop(cf.postprocess_dropout, sv.s_post);
+  e1.drop = c.drop(cf.postprocess_dropout, sv.s_post, (int64_t)M * d);
   e1.residual = x_in; e1.res_ld = d;
   B200ST_TRY(linear_fwd(c, sv.ctx, d, M, d, d, pre + ".out.kernel", pre + ".out.bias", e1, x_out, F32, d));
   return 0;
@@ -467,10 +481,10 @@ static int ffn_block_fwd(Ctx& c, const std::string& pre, const float* x_in, floa
                     M, d, 0, c.st));
   GemmEpilogue e1 = gemm_defaults().epi;
   e1.relu = 1;
-  e1.drop = c.drop(cf.ffn_dropout, sv.s_ffn);
+  e1.drop = c.drop(cf.ffn_dropout, sv.s_ffn, (int64_t)M * f);
   B200ST_TRY(linear_fwd(c, sv.h, d, M, d, f, pre + ".w1", pre + ".b1", e1, sv.f1, c.adt, f));
   GemmEpilogue e2 = gemm_defaults().epi;
-  e2.drop = c.drop(cf.postprocess_dropout, sv.s_post);
+  e2.drop = c.drop(cf.postprocess_dropout, sv.s_post, (int64_t)M * d);
   e2.residual = x_in; e2.res_ld = d;
   B200ST_TRY(linear_fwd(c, sv.f1, f, M, f, d, pre + ".w2", pre + ".b2", e2, x_out, F32, d));
   return 0;
@@ -649,7 +663,7 @@ static int speech_front_fwd(Ctx& c, const float* src, int B, int T, float* x0, F
   }
   GemmEpilogue ed = gemm_defaults().epi;
   B200ST_TRY(linear_fwd(c, sv.y2, (int64_t)F2 * C, B * T2, F2 * C, d, "src.dense.kernel", "src.dense.bias", ed, e0, F32, d));
-  RUN(posenc_fwd(e0, x0, B, T2, d, sqrtf((float)d), 0, c.drop(cf.postprocess_dropout, sv.s_in), c.st));
+  RUN(posenc_fwd(e0, x0, B, T2, d, sqrtf((float)d), 0, c.drop(cf.postprocess_dropout, sv.s_in, (int64_t)B * T2 * d), c.st));
   return 0;
 }
 
@@ -817,7 +831,9 @@ static int run_planned(const Model& m, const Buffers& buf, cudaStream_t st, F&& 
                                                 std::to_string(buf.workspace_bytes));
   if (m.adt == BF16) B200ST_CHECK(buf.shadow != nullptr, "bf16 precision needs the bf16 shadow arena");
   Ctx real(m, buf, st, false);
-  return body(real);
+  B200ST_TRY(body(real));
+  B200ST_CHECK(!real.launch_failed, "dropout bitmap kernel launch failed");
+  return 0;
 }
 
 }  // namespace

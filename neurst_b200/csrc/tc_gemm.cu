@@ -163,7 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_in_tile = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const GemmEpilogue& ep = p.epi;
-    const bool drop_vec_ok = ep.drop.p == 0.f || (p.N % 8 == 0);       // dropout groups of 8 stay row-aligned
+    const bool drop_vec_ok = ep.drop.p == 0.f || (ep.drop.bits ? (p.N % 32 == 0) : (p.N % 8 == 0));   // groups stay row-aligned
     const uint32_t drop_thresh = dropout_thresh16(ep.drop.p);
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -239,9 +239,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (ep.drop.p > 0.f) {
             const uint64_t e0 = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n0);
+            uint32_t keep32 = 0;
+            const bool have_bits = ep.drop.bits != nullptr;
+            if (have_bits) keep32 = __ldg(reinterpret_cast<const uint32_t*>(ep.drop.bits + (e0 >> 3)));   // N % 32 == 0 here
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
-              const uint32_t keep = dropout_keep8(dropout_seed(ep.drop), ep.drop.stream, (e0 >> 3) + g8, drop_thresh);
+              const uint32_t keep = have_bits ? (keep32 >> (8 * g8)) : dropout_keep8(dropout_seed(ep.drop), ep.drop.stream, (e0 >> 3) + g8, drop_thresh);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[8 * g8 + j] = ((keep >> j) & 1u) ? v[8 * g8 + j] * ep.drop.scale : 0.f;
             }
