@@ -79,6 +79,7 @@ struct TcDebug {
   int force_bn;     // 0 = auto
   int force_stages; // 0 = auto
   int max_ctas;     // 0 = #SMs
+  int one_cta_per_sm; // 1 = disable the 2-CTAs-per-SM mode of the BN <= 128 variants
 };
 TcDebug& tc_debug();
 int64_t tc_launch_count();

@@ -27,6 +27,7 @@ constexpr int BK = 64;                  // 64 bf16 = 128 B = one swizzle row
 constexpr int kThreads = 320;              // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemLimit = 232448;      // 227 KB
 constexpr uint32_t kABytes = BM * BK * 2;
+constexpr uint32_t kStagingBytes = 8 * 2 * 4096;   // per epilogue warp: two 32-row x 128-byte boxes (ping-pong)
 
 struct TcParams {
   int M, N, K;
@@ -42,6 +43,9 @@ struct TcParams {
   int64_t ldc, c_sb1, c_sb2;
   GemmEpilogue epi;
   int atomic;
+  int use_tma_store;    // epilogue writes C through per-warp smem boxes + TMA store (aligned, non-ragged tiles)
+  int c_reduce;         // C += (atomic / accumulate): cp.reduce.async.bulk.tensor .add
+  long long* dbg_trace; // perf experiments only: [cta][tile][8] clock64 stamps
 };
 
 struct TileCoord { int b2, b1, m_blk, n_blk, split; };
@@ -56,9 +60,130 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
   return t;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC = 2 };
+
+// Cold path (ragged N, unaligned rows, on-the-fly Philox): compact, not unrolled, out of line — keeps the kernel's hot
+// code small enough for the instruction cache (the first version inlined every variant: 17 k SASS instructions).
+__device__ __noinline__ void epilogue_chunk_general(const TcParams& p, const float* acc, int m, int n0, int64_t bidx,
+                                                    int64_t boff_c, int64_t boff_mask, int64_t boff_res) {
+  const GemmEpilogue& ep = p.epi;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const int n = n0 + j;
+    if (n >= p.N) break;
+    const uint64_t e_idx = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n);
+    const float v = gemm_epilogue_value(ep, acc[j], m, n, boff_mask, boff_res, e_idx);
+    const int64_t idx = boff_c + (int64_t)m * p.ldc + n;
+    if (p.atomic) atomicAdd(reinterpret_cast<float*>(p.C) + idx, v);
+    else if (p.c_dtype == F32) reinterpret_cast<float*>(p.C)[idx] = ep.accumulate ? reinterpret_cast<float*>(p.C)[idx] + v : v;
+    else reinterpret_cast<__nv_bfloat16*>(p.C)[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// Per-row epilogue context: everything that does not change between the 32-column chunks of one tile row.
+struct EpiRow {
+  const float* bias;    // at n_base or null
+  const char* mask;     // at n_base or null
+  const float* res;     // at n_base or null
+  const uint8_t* bits;  // dropout keep-bits at element (row, n_base) or null
+  bool row_ok;          // m < M (rows beyond M are clipped by the TMA store; their loads are skipped)
+};
+
+// alpha / bias / relu / relu-mask / dropout bits / residual on one 32-column chunk (thread = one output row)
+template <int OUT>
+__device__ __forceinline__ void epilogue_math(const TcParams& p, const uint32_t (&r)[32], const EpiRow& e, int co, float relu_floor,
+                                              float (&v)[32]) {
+  const GemmEpilogue& ep = p.epi;
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + co);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 bb = __ldg(b4 + j);
+      v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(r[4 * j + 0]), ep.alpha, bb.x), relu_floor);
+      v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), ep.alpha, bb.y), relu_floor);
+      v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), ep.alpha, bb.z), relu_floor);
+      v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), ep.alpha, bb.w), relu_floor);
+    }
+  } else if (ep.relu || ep.alpha != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) * ep.alpha, relu_floor);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  }
+  if (OUT == OUT_ATOMIC || !e.row_ok) return;
+  if (e.mask) {
+    if (ep.mask_dtype == BF16) {
+      const uint4* mp = reinterpret_cast<const uint4*>(e.mask + co * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 pk = __ldg(mp + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          if (!(f.x > 0.f)) v[8 * j + 2 * i] = 0.f;
+          if (!(f.y > 0.f)) v[8 * j + 2 * i + 1] = 0.f;
+        }
+      }
+    } else {
+      const float4* mp = reinterpret_cast<const float4*>(e.mask + co * 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 f = __ldg(mp + j);
+        if (!(f.x > 0.f)) v[4 * j] = 0.f;
+        if (!(f.y > 0.f)) v[4 * j + 1] = 0.f;
+        if (!(f.z > 0.f)) v[4 * j + 2] = 0.f;
+        if (!(f.w > 0.f)) v[4 * j + 3] = 0.f;
+      }
+    }
+  }
+  if (e.bits) {
+    const uint32_t keep32 = __ldg(reinterpret_cast<const uint32_t*>(e.bits + (co >> 3)));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((keep32 >> j) & 1u) ? v[j] * ep.drop.scale : 0.f;
+  }
+  if (e.res) {
+    const float4* rp = reinterpret_cast<const float4*>(e.res + co);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 rr = __ldg(rp + j);
+      v[4 * j + 0] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+    }
+  }
+}
+
+// Writes this lane's row of a 32-column chunk into the warp's staging box ([32 rows x 128 B], 128B-swizzled, i.e. the
+// layout the C tensor map expects): bf16 = half a row (64 B) at chunk-in-box `cb`, fp32 = the whole 128-byte row.
+template <int OUT>
+__device__ __forceinline__ void stage_chunk(uint32_t buf, int lane, int cb, const float (&v)[32]) {
+  const uint32_t row = buf + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  if (OUT == OUT_BF16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+      const uint32_t addr = row + ((((uint32_t)(cb * 4 + j)) ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                   "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t addr = row + ((((uint32_t)j) ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])),
+                   "r"(__float_as_uint(v[4 * j + 2])), "r"(__float_as_uint(v[4 * j + 3]))
+                   : "memory");
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int OUT>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kBBytes = BN * BK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -66,7 +191,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stages = p.stages;
-  const uint32_t bar_base = smem_base + stages * kStageBytes;   // 8-byte barriers
+  const uint32_t stage_out = smem_base + stages * kStageBytes;   // 8 warps x 2 x 4 KB epilogue staging boxes
+  const uint32_t bar_base = stage_out + kStagingBytes;           // 8-byte barriers
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
@@ -81,6 +207,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (p.use_tma_store) ptx::prefetch_tensormap(&tmC);
     for (int s = 0; s < stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 8); }
     ptx::fence_mbar_init();
@@ -102,8 +229,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TileCoord t = decode_tile(p, tile);
         const int kb0 = t.split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        int tix = (int)((tile - blockIdx.x) / gridDim.x);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (p.dbg_trace && kb == kb0 && tix < 8) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 0] = clock64();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
           ptx::mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
@@ -134,12 +263,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TileCoord t = decode_tile(p, tile);
         const int kb0 = t.split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        int tix = (int)((tile - blockIdx.x) / gridDim.x);
+        if (p.dbg_trace && tix < 8) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 1] = clock64();
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
+        if (p.dbg_trace && tix < 8) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 2] = clock64();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
+          if (p.dbg_trace && tix < 8 && kb == kb0) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 3] = clock64();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
 #pragma unroll
@@ -152,6 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         ptx::mma_commit(tfull_bar(acc));         // accumulator ready for the epilogue warps
+        if (p.dbg_trace && tix < 8) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -163,178 +297,92 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_in_tile = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const GemmEpilogue& ep = p.epi;
-    const bool drop_vec_ok = ep.drop.p == 0.f || (ep.drop.bits ? (p.N % 32 == 0) : (p.N % 8 == 0));   // groups stay row-aligned
-    const uint32_t drop_thresh = dropout_thresh16(ep.drop.p);
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
+      const int tix = (int)((tile - blockIdx.x) / gridDim.x);
+      if (p.dbg_trace && tix < 8 && warp == 2 && lane == 0) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 5] = clock64();
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
+      if (p.dbg_trace && tix < 8 && warp == 2 && lane == 0) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 6] = clock64();
       const int m = t.m_blk * BM + row_in_tile;
       const int64_t bidx = (int64_t)t.b2 * p.nb1 + t.b1;
       const int64_t boff_c = (int64_t)t.b2 * p.c_sb2 + (int64_t)t.b1 * p.c_sb1;
       const int64_t boff_mask = (int64_t)t.b2 * ep.mask_sb2 + (int64_t)t.b1 * ep.mask_sb1;
       const int64_t boff_res = (int64_t)t.b2 * ep.res_sb2 + (int64_t)t.b1 * ep.res_sb1;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const int n_base = t.n_blk * BN;
+      const int c_begin = half * (BN / 2);
+      const bool tile_tma = p.use_tma_store && (n_base + BN <= p.N);     // warp-uniform
+      if (tile_tma) {
+        // ---- TMA-store path: TMEM -> registers -> fused math -> swizzled smem box -> cp.async.bulk.tensor store ----
+        EpiRow er;
+        er.row_ok = m < p.M;
+        er.bias = ep.bias ? ep.bias + n_base : nullptr;
+        er.mask = (ep.mask_src && er.row_ok) ? reinterpret_cast<const char*>(ep.mask_src) +
+                                                   (size_t)(boff_mask + (int64_t)m * ep.mask_ld + n_base) * (ep.mask_dtype == BF16 ? 2 : 4)
+                                             : nullptr;
+        er.res = (ep.residual && er.row_ok) ? ep.residual + boff_res + (int64_t)m * ep.res_ld + n_base : nullptr;
+        er.bits = (ep.drop.p > 0.f && er.row_ok) ? ep.drop.bits + ((uint64_t)((bidx * p.M + m) * (int64_t)p.N + n_base) >> 3) : nullptr;
+        constexpr int kColsPerBox = (OUT == OUT_BF16) ? 64 : 32;
+        // BN = 64 with bf16 output: one 64-column box per quadrant, written by the half-0 warp alone
+        constexpr bool kSingle = (BN / 2 < kColsPerBox);
+        constexpr int kBoxes = kSingle ? 1 : BN / 2 / kColsPerBox;
+        const int c_begin_box = kSingle ? 0 : c_begin;
+        const int n_boxes = (kSingle && half == 1) ? 0 : kBoxes;
+        const uint32_t my_stage = stage_out + (uint32_t)(warp - 2) * 8192u;
 #pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-        const int n0 = t.n_blk * BN + c0;
-        if (n0 >= p.N) break;                     // warp-uniform
-        uint32_t r[32];
-        __syncwarp();
-        ptx::tmem_ld_32x32b_x32(taddr_row + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        if (m < p.M) {
-        const bool full = (n0 + 32 <= p.N);
-        float v[32];
-        const char* mask_row = ep.mask_src
-            ? reinterpret_cast<const char*>(ep.mask_src) + (size_t)(boff_mask + (int64_t)m * ep.mask_ld + n0) * (ep.mask_dtype == BF16 ? 2 : 4)
-            : nullptr;
-        const bool fast = full && drop_vec_ok && ((reinterpret_cast<uintptr_t>(mask_row) & 15) == 0);
-        if (fast) {
-          // ---- fast path: alpha, bias, relu branch-free; mask / dropout / residual vectorised ----
-          if (ep.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);   // n0 % 32 == 0, arena 32B-aligned
-            if ((reinterpret_cast<uintptr_t>(b4) & 15) == 0) {
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          const uint32_t buf = my_stage + (uint32_t)(bx & 1) * 4096u;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box written 2 iterations ago is drained
+          __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(b4 + j);
-                v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(r[4 * j + 0]), ep.alpha, bb.x), relu_floor);
-                v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(r[4 * j + 1]), ep.alpha, bb.y), relu_floor);
-                v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(r[4 * j + 2]), ep.alpha, bb.z), relu_floor);
-                v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(r[4 * j + 3]), ep.alpha, bb.w), relu_floor);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                v[j] = fmaxf(fmaf(__uint_as_float(r[j]), ep.alpha, __ldg(ep.bias + n0 + j)), relu_floor);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) * ep.alpha, relu_floor);
+          for (int cb = 0; cb < kColsPerBox / 32; ++cb) {
+            const int co = c_begin_box + bx * kColsPerBox + cb * 32;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr_row + (uint32_t)co, r);
+            ptx::tmem_ld_wait();
+            float v[32];
+            epilogue_math<OUT>(p, r, er, co, relu_floor, v);
+            stage_chunk<OUT>(buf, lane, cb, v);
           }
-          if (mask_row) {
-            if (ep.mask_dtype == BF16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(mask_row) + j);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __bfloat1622float2(h[i]);
-                  if (!(f.x > 0.f)) v[8 * j + 2 * i] = 0.f;
-                  if (!(f.y > 0.f)) v[8 * j + 2 * i + 1] = 0.f;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(mask_row) + j);
-                if (!(f.x > 0.f)) v[4 * j] = 0.f;
-                if (!(f.y > 0.f)) v[4 * j + 1] = 0.f;
-                if (!(f.z > 0.f)) v[4 * j + 2] = 0.f;
-                if (!(f.w > 0.f)) v[4 * j + 3] = 0.f;
-              }
-            }
-          }
-          if (ep.drop.p > 0.f) {
-            const uint64_t e0 = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n0);
-            uint32_t keep32 = 0;
-            const bool have_bits = ep.drop.bits != nullptr;
-            if (have_bits) keep32 = __ldg(reinterpret_cast<const uint32_t*>(ep.drop.bits + (e0 >> 3)));   // N % 32 == 0 here
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const uint32_t keep = have_bits ? (keep32 >> (8 * g8)) : dropout_keep8(dropout_seed(ep.drop), ep.drop.stream, (e0 >> 3) + g8, drop_thresh);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[8 * g8 + j] = ((keep >> j) & 1u) ? v[8 * g8 + j] * ep.drop.scale : 0.f;
-            }
-          }
-          if (ep.residual) {
-            const float* rp = ep.residual + boff_res + (int64_t)m * ep.res_ld + n0;
-            if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(rp) + j);
-                v[4 * j + 0] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(rp + j);
-            }
-          }
-        } else {
-          // ---- general path: relu-mask source, dropout, ragged N ----
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            const uint64_t e_idx = (uint64_t)((bidx * p.M + m) * (int64_t)p.N + n);
-            v[j] = (n < p.N) ? gemm_epilogue_value(ep, __uint_as_float(r[j]), m, n, boff_mask, boff_res, e_idx) : 0.f;
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int cn = n_base + c_begin_box + bx * kColsPerBox, cm = t.m_blk * BM + quad * 32;
+            if (p.c_reduce)
+              asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(&tmC), "r"(buf), "r"(cn), "r"(cm), "r"(t.b1), "r"(t.b2) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(&tmC), "r"(buf), "r"(cn), "r"(cm), "r"(t.b1), "r"(t.b2) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        const int64_t row_off = boff_c + (int64_t)m * p.ldc + n0;
-        if (p.atomic) {
-          float* c = reinterpret_cast<float*>(p.C) + row_off;
-          if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+      } else {
+        // ---- general path (ragged N, unaligned operands, on-the-fly Philox): per-element, compact ----
+#pragma unroll 1
+        for (int co = c_begin; co < c_begin + BN / 2; co += 32) {
+          if (n_base + co >= p.N) break;
+          uint32_t r[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32b_x32(taddr_row + (uint32_t)co, r);
+          ptx::tmem_ld_wait();
+          if (m < p.M) {
+            float acc_v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
-                           "f"(v[j + 3]) : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) atomicAdd(c + j, v[j]);
-          }
-        } else if (p.c_dtype == F32) {
-          float* c = reinterpret_cast<float*>(p.C) + row_off;
-          if (ep.accumulate) {
-            if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = *reinterpret_cast<float4*>(c + j);
-                o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
-                *reinterpret_cast<float4*>(c + j) = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) c[j] += v[j];
-            }
-          } else if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) c[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + row_off;
-          if (full && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(c + j) = pk;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) c[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j) acc_v[j] = __uint_as_float(r[j]);
+            epilogue_chunk_general(p, acc_v, m, n_base + co, bidx, boff_c, boff_mask, boff_res);
           }
         }
-        }  // m < M
       }
       ptx::tc_fence_before();
       __syncwarp();
+      if (p.dbg_trace && tix < 8 && warp == 2 && lane == 0) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 7] = clock64();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all of this warp's TMA stores are complete
   }
 
   ptx::tc_fence_before();
@@ -414,6 +462,37 @@ int make_operand_map(const GemmOperand& op, int rows, int K, int nb1, int nb2, i
   return 0;
 }
 
+// Output tensor map: dims (N, M, nb1, nb2); box = {128 bytes of columns, 32 rows} (one epilogue warp), 128B swizzle.
+int make_out_map(const void* C, int c_dtype, int N, int M, int nb1, int nb2, int64_t ldc, int64_t sb1, int64_t sb2, CUtensorMap* out) {
+  EncodeTiledFn fn = get_encode_fn();
+  B200ST_CHECK(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const uint64_t es = c_dtype == F32 ? 4 : 2;
+  uint64_t s1 = nb1 > 1 ? (uint64_t)sb1 : (uint64_t)ldc * M;
+  uint64_t s2 = nb2 > 1 ? (uint64_t)sb2 : s1 * (uint64_t)nb1;
+  if (s1 == 0) s1 = (uint64_t)ldc * M;
+  if (s2 == 0) s2 = s1 * (uint64_t)nb1;
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)ldc * es, s1 * es, s2 * es};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / es), 32u, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  if (strides[1] % 16 != 0) strides[1] = (strides[1] + 15) / 16 * 16;   // size-1 batch dims: any legal stride
+  if (strides[2] % 16 != 0) strides[2] = (strides[2] + 15) / 16 * 16;
+  MapKey key{{(uint64_t)(uintptr_t)C, (uint64_t)N, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2, strides[0], strides[1], strides[2],
+              0x1000u + es, 7u}};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return 0; }
+  }
+  CUresult r = fn(out, c_dtype == F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(C), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) B200ST_FAIL("cuTensorMapEncodeTiled (output) failed with CUresult " + std::to_string((int)r));
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  g_map_cache.emplace(key, *out);
+  return 0;
+}
+
 int g_num_sms = 0;
 int64_t g_launches = 0;
 }  // namespace
@@ -433,27 +512,35 @@ struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, batch, bn, split
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
 
-template <int BN, bool A_MN, bool B_MN>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int grid, size_t smem,
-                   cudaStream_t stream) {
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN>;
+template <int BN, bool A_MN, bool B_MN, int OUT>
+int launch_out(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, int grid, size_t smem,
+               cudaStream_t stream) {
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, OUT>;
   static bool attr_set = false;
   if (!attr_set) {
     B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(ta, tb, p);
+  kern<<<grid, kThreads, smem, stream>>>(ta, tb, tc, p);
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, int grid, size_t smem,
+                   cudaStream_t stream) {
+  if (p.atomic) return launch_out<BN, A_MN, B_MN, OUT_ATOMIC>(ta, tb, tc, p, grid, smem, stream);
+  if (p.c_dtype == F32) return launch_out<BN, A_MN, B_MN, OUT_F32>(ta, tb, tc, p, grid, smem, stream);
+  return launch_out<BN, A_MN, B_MN, OUT_BF16>(ta, tb, tc, p, grid, smem, stream);
+}
+
 template <int BN>
-int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, int grid,
+int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcParams& p, int grid,
               size_t smem, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, p, grid, smem, stream);
-  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, p, grid, smem, stream);
-  if (a_mn && !b_mn) return launch_variant<BN, true, false>(ta, tb, p, grid, smem, stream);
-  return launch_variant<BN, true, true>(ta, tb, p, grid, smem, stream);
+  if (!a_mn && !b_mn) return launch_variant<BN, false, false>(ta, tb, tc, p, grid, smem, stream);
+  if (!a_mn && b_mn) return launch_variant<BN, false, true>(ta, tb, tc, p, grid, smem, stream);
+  if (a_mn && !b_mn) return launch_variant<BN, true, false>(ta, tb, tc, p, grid, smem, stream);
+  return launch_variant<BN, true, true>(ta, tb, tc, p, grid, smem, stream);
 }
 
 }  // namespace
@@ -504,6 +591,7 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   splitk = ceil_div(p.kb_total, p.kb_per_split);   // no empty trailing split
   p.splitk = splitk;
   p.atomic = (splitk > 1) ? 1 : 0;
+  p.dbg_trace = getenv("B200ST_DEBUG_TRACE_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("B200ST_DEBUG_TRACE_PTR"), nullptr, 0)) : nullptr;
 
   // ---- BN selection: fewest waves x per-tile cycles.  Per k-block a CTA needs max(tensor time, L2->smem fill time):
   // 4 MMAs of 128 x c x 16 take 2c cycles; the operand bytes (16 KB + 128c B) arrive at ~44 B/cycle/SM (measured:
@@ -527,10 +615,12 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.num_tiles = batch * p.m_tiles * p.n_tiles * splitk;
 
   const uint32_t stage_bytes = kABytes + (uint32_t)bn * BK * 2;
-  int stages = dbg.force_stages > 0 ? dbg.force_stages : (int)((kSmemLimit - 2048) / stage_bytes);
+  const int ctas_per_sm = 1;   // (two co-resident CTAs per SM were measured: no gain, see profiles/r01_gemm_notes.md)
+  const int smem_budget = (ctas_per_sm == 2 ? (kSmemLimit / 2 - 1024) : kSmemLimit) - (int)kStagingBytes;
+  int stages = dbg.force_stages > 0 ? dbg.force_stages : (int)((smem_budget - 2048) / stage_bytes);
   if (stages > 8) stages = 8;
   p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 5) + 16;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 8 * (2 * stages + 5) + 16;
   B200ST_CHECK(smem <= (size_t)kSmemLimit, "smem budget exceeded");
 
   // descriptors
@@ -548,11 +638,33 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.epi = g.epi;
   if (g.epi.accumulate) B200ST_CHECK(g.c_dtype == F32, "accumulate needs fp32 C");
 
+  // ---- output path: TMA store through per-warp staging boxes when everything is 16-byte aligned ----
+  const uint64_t esz_c = g.c_dtype == F32 ? 4 : 2;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  bool tma_ok = al16(g.C) && (g.ldc * esz_c) % 16 == 0 && (g.nb1 == 1 || (g.c_sb1 * esz_c) % 16 == 0) &&
+                (g.nb2 == 1 || (g.c_sb2 * esz_c) % 16 == 0) && g.N >= bn;
+  if (g.epi.bias) tma_ok = tma_ok && al16(g.epi.bias);
+  if (g.epi.mask_src) {
+    const uint64_t em = g.epi.mask_dtype == F32 ? 4 : 2;
+    tma_ok = tma_ok && al16(g.epi.mask_src) && (g.epi.mask_ld * em) % 16 == 0 && (g.epi.mask_sb1 * em) % 16 == 0 &&
+             (g.epi.mask_sb2 * em) % 16 == 0;
+  }
+  if (g.epi.residual)
+    tma_ok = tma_ok && al16(g.epi.residual) && (g.epi.res_ld * 4) % 16 == 0 && (g.epi.res_sb1 * 4) % 16 == 0 && (g.epi.res_sb2 * 4) % 16 == 0;
+  if (g.epi.drop.p > 0.f) tma_ok = tma_ok && g.epi.drop.bits != nullptr && (g.N % 32 == 0);
+  if (getenv("B200ST_NO_TMA_STORE")) tma_ok = false;
+  p.use_tma_store = tma_ok ? 1 : 0;
+  p.c_reduce = (p.atomic || g.epi.accumulate) ? 1 : 0;
+  CUtensorMap tc;
+  std::memset(&tc, 0, sizeof(tc));
+  if (tma_ok) B200ST_TRY(make_out_map(g.C, g.c_dtype, g.N, g.M, g.nb1, g.nb2, g.ldc, g.c_sb1, g.c_sb2, &tc));
+
   CUtensorMap ta, tb;
   B200ST_TRY(make_operand_map(g.A, g.M, g.K, g.nb1, g.nb2, BM, &ta));
   B200ST_TRY(make_operand_map(g.B, g.N, g.K, g.nb1, g.nb2, bn, &tb));
 
-  const int grid = (int)(p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  const int max_grid = num_sms * ctas_per_sm;
+  const int grid = (int)(p.num_tiles < max_grid ? p.num_tiles : max_grid);
   ++g_launches;
   ProfRec rec{};
   if (g_prof) {
@@ -567,9 +679,9 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   }
   int rc = 0;
   switch (bn) {
-    case 64: rc = launch_bn<64>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream); break;
-    case 128: rc = launch_bn<128>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream); break;
-    case 256: rc = launch_bn<256>(g.A.mn_major, g.B.mn_major, ta, tb, p, grid, smem, stream); break;
+    case 64: rc = launch_bn<64>(g.A.mn_major, g.B.mn_major, ta, tb, tc, p, grid, smem, stream); break;
+    case 128: rc = launch_bn<128>(g.A.mn_major, g.B.mn_major, ta, tb, tc, p, grid, smem, stream); break;
+    case 256: rc = launch_bn<256>(g.A.mn_major, g.B.mn_major, ta, tb, tc, p, grid, smem, stream); break;
     default: B200ST_FAIL("unsupported BN");
   }
   if (g_prof && rc == 0) {
