@@ -233,6 +233,13 @@ def run_gpu(args):
         gms, gfl, gn = lib.profile_end()
         gemm = dict(ms=gms, flops=gfl, launches=gn)
     barrier()
+    # kernels per step: counted on one eagerly launched step (a CUDA-graph replay re-issues the same kernel nodes)
+    trainer.use_cuda_graph = False
+    l0 = lib.launch_count()
+    resident_step(1)
+    torch.cuda.synchronize()
+    launches_per_step = lib.launch_count() - l0
+    barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -258,13 +265,13 @@ def run_gpu(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "SpeechTransformer-base (speech_transformer_s: conv2d subsample + 12enc/6dec, d=256) synthetic "
                                "fbank [32,1000,80] per GPU, L=88, V=8192, dropout 0.1, label_smoothing 0.1, Adam+noam",
-                   "global_batch_frames": frames, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+                   "global_batch_frames": frames, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "kernels_per_step": int(launches_per_step),
                    "l2_policy": "inputs+activations per step (~4 GB) exceed the 126 MB L2; 4 rotating input batches",
                    "loss_last_step": loss_val},
         "clocks": clocks,
         "e2e": {"value": frames / (ms_e2e / args.steps * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": ach / peaks["tflops_sustained"], "traffic": None, "peak_source": peaks["source"],
                      "algorithmic_flops_per_step": fl, "mflop_per_frame": fl / (B * T) / 1e6,

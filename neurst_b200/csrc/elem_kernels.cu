@@ -839,6 +839,24 @@ int dropout_bits(DropoutSpec drop, int64_t n_elems, uint8_t* out, cudaStream_t s
   B200ST_LAUNCH_CHECK();
   return 0;
 }
+__global__ void __launch_bounds__(256) dropout_bits_multi_kernel(const DropBitsTable t, uint64_t seed, const uint64_t* seed_ptr,
+                                                                  uint8_t* __restrict__ base) {
+  const uint64_t sd = seed_ptr ? *seed_ptr : seed;
+  const int64_t total = t.goff[t.n];
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = t.n - 1;                      // last site whose first group <= g
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (t.goff[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int64_t local = g - t.goff[lo];
+    base[t.boff[lo] + local] = (uint8_t)dropout_keep8(sd, t.stream[lo], (uint64_t)local, t.thresh[lo]);
+  }
+}
+int dropout_bits_multi(const DropBitsTable& t, uint64_t seed, const uint64_t* seed_ptr, uint8_t* base, cudaStream_t s) {
+  if (t.n == 0 || t.goff[t.n] == 0) return 0;
+  dropout_bits_multi_kernel<<<grid_for(t.goff[t.n], 256, 148 * 8), 256, 0, s>>>(t, seed, seed_ptr, base);
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);

@@ -60,6 +60,15 @@ int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int
               float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s);
 // out[g] = keep-bits of elements [8g, 8g+8) of the dropout site (identical to the on-the-fly Philox decisions)
 int dropout_bits(DropoutSpec drop, int64_t n_elems, uint8_t* out, cudaStream_t s);
+// all dropout sites of a step in one launch: site i covers groups [goff[i], goff[i+1]) and writes base[boff[i] + local]
+struct DropBitsTable {
+  int n;
+  uint64_t stream[128];
+  uint32_t thresh[128];
+  int64_t goff[129];
+  int64_t boff[128];
+};
+int dropout_bits_multi(const DropBitsTable& t, uint64_t seed, const uint64_t* seed_ptr, uint8_t* base, cudaStream_t s);
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s);
 int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 

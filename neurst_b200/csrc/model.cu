@@ -154,6 +154,9 @@ struct Ctx {
   float* f32(int64_t n) { return reinterpret_cast<float*>(ar.take((size_t)n * 4)); }
   std::unordered_map<uint64_t, DropoutSpec> drop_memo;
   bool launch_failed = false;
+  struct DropSite { uint64_t stream; float p; int64_t groups; size_t arena_off; };
+  std::vector<DropSite> drop_sites;      // recorded in allocation order (planning pass -> one batched generator launch)
+  bool bits_pregenerated = false;
   // Dropout site `stream`.  The first (forward) use passes the element count: the keep-bits of the whole site are then
   // generated once into the workspace (one Philox call per 8 elements, full-occupancy kernel) and every consumer —
   // GEMM epilogues, fused attention, the backward pass — just reads bits.  Later uses return the memoised spec.
@@ -164,7 +167,8 @@ struct Ctx {
     DropoutSpec d{p, 1.f / (1.f - p), seed, stream, seed_dev, nullptr};
     if (n_elems > 0) {
       uint8_t* bits = reinterpret_cast<uint8_t*>(ar.take((size_t)((n_elems + 7) / 8 + 4)));
-      if (!dry && dropout_bits(d, n_elems, bits, st) != 0) launch_failed = true;
+      drop_sites.push_back(DropSite{stream, p, (n_elems + 7) / 8, (size_t)(reinterpret_cast<char*>(bits) - ar.base)});
+      if (!dry && !bits_pregenerated && dropout_bits(d, n_elems, bits, st) != 0) launch_failed = true;
       d.bits = bits;
       drop_memo[stream] = d;
     }
@@ -831,8 +835,29 @@ static int run_planned(const Model& m, const Buffers& buf, cudaStream_t st, F&& 
                                                 std::to_string(buf.workspace_bytes));
   if (m.adt == BF16) B200ST_CHECK(buf.shadow != nullptr, "bf16 precision needs the bf16 shadow arena");
   Ctx real(m, buf, st, false);
+  // All dropout keep-bits of the call in ONE launch: the planning pass recorded every site in allocation order (the real
+  // pass allocates identically), the table travels as a kernel argument.
+  if (!dry.drop_sites.empty() && dry.drop_sites.size() <= 128) {
+    DropBitsTable t{};
+    t.n = (int)dry.drop_sites.size();
+    int64_t g = 0;
+    for (int i = 0; i < t.n; ++i) {
+      const auto& ds = dry.drop_sites[i];
+      t.stream[i] = ds.stream; t.thresh[i] = dropout_thresh16(ds.p); t.goff[i] = g; t.boff[i] = (int64_t)ds.arena_off;
+      g += ds.groups;
+    }
+    t.goff[t.n] = g;
+    B200ST_TRY(dropout_bits_multi(t, dry.seed, dry.seed_dev, reinterpret_cast<uint8_t*>(buf.workspace), st));
+    real.bits_pregenerated = true;
+  }
   B200ST_TRY(body(real));
   B200ST_CHECK(!real.launch_failed, "dropout bitmap kernel launch failed");
+  if (real.bits_pregenerated) {
+    B200ST_CHECK(real.drop_sites.size() == dry.drop_sites.size(), "dropout site plan mismatch");
+    for (size_t i = 0; i < real.drop_sites.size(); ++i)
+      B200ST_CHECK(real.drop_sites[i].arena_off == dry.drop_sites[i].arena_off && real.drop_sites[i].stream == dry.drop_sites[i].stream,
+                   "dropout site plan mismatch");
+  }
   return 0;
 }
 

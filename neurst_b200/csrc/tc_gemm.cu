@@ -568,49 +568,52 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.kb_total = ceil_div(g.K, BK);
   const int64_t batch = (int64_t)g.nb1 * g.nb2;
 
-  // ---- split-K (only for linear fp32 accumulation epilogues) ----
-  int splitk = g.splitk;
+  // ---- joint choice of the N tile and the split-K factor ----
+  // Per k-block a CTA needs max(tensor time, L2->smem fill time): 4 MMAs of 128 x c x 16 take 2c cycles; the operand
+  // bytes (16 KB + 128c B) arrive at ~44 B/cycle/SM (measured, profiles/r01_gemm_notes.md).  The epilogue overlaps the
+  // next tile's main loop.  Split-K (fp32 TMA reduce-add epilogue) is allowed for linear accumulate epilogues only and is
+  // chosen so that the tile count fills the 148 SMs once.
   const bool linear_epi = !g.epi.relu && !g.epi.mask_src && g.epi.drop.p == 0.f && !g.epi.residual && !g.epi.bias;
-  if (splitk == 0) {   // auto
-    splitk = 1;
-    if (linear_epi && g.c_dtype == F32 && g.epi.accumulate) {
-      const int64_t base_tiles = batch * p.m_tiles * ceil_div(g.N, 128);
-      while (base_tiles * splitk * 2 <= num_sms && p.kb_total / (splitk * 2) >= 4) splitk *= 2;
-      if (base_tiles * splitk < num_sms && p.kb_total / splitk >= 8) {
-        int want = (int)((num_sms + base_tiles - 1) / base_tiles);
-        int maxs = p.kb_total / 4;
-        splitk = want < maxs ? want : (maxs > 0 ? maxs : 1);
+  const bool split_ok = linear_epi && g.c_dtype == F32 && g.epi.accumulate;
+  if (g.splitk > 1) B200ST_CHECK(split_ok, "split-K needs a linear fp32 accumulate epilogue");
+  int bn = dbg.force_bn, splitk = g.splitk >= 1 ? g.splitk : 1;
+  {
+    double best = 1e30;
+    int best_bn = 0, best_sk = 1;
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+      if (dbg.force_bn && c != dbg.force_bn) continue;
+      if (!dbg.force_bn && c > 64 && c >= 2 * ((g.N + 63) / 64 * 64)) continue;   // do not pad N by 2x or more
+      const int64_t tiles0 = batch * p.m_tiles * ceil_div(g.N, c);
+      int sk_lo = splitk, sk_hi = splitk;
+      if (g.splitk == 0 && split_ok) {
+        sk_lo = 1;
+        sk_hi = (int)(num_sms / tiles0);
+        const int cap = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
+        if (sk_hi > cap) sk_hi = cap;
+        if (sk_hi < 1) sk_hi = 1;
+      }
+      for (int sk = sk_hi; sk >= sk_lo; sk = (sk > sk_lo && sk > 1) ? (sk == sk_hi && sk_hi > 2 ? sk / 2 : sk - 1) : sk_lo - 1) {
+        const int kb_per = ceil_div(p.kb_total, sk);
+        const int64_t tiles = tiles0 * ceil_div(p.kb_total, kb_per);
+        const int64_t waves = (tiles + num_sms - 1) / num_sms;
+        const double fill = (16384.0 + 128.0 * c) / 44.0, mma = 2.0 * c;
+        const double mainloop = kb_per * (fill > mma ? fill : mma);
+        const double epi = (sk > 1 ? 14.0 : 10.0) * c + 600.0;
+        const double cost = (double)waves * ((mainloop > epi ? mainloop : epi) + 800.0) + (sk > 1 ? 500.0 : 0.0);
+        if (cost < best) { best = cost; best_bn = c; best_sk = sk; }
+        if (sk <= sk_lo) break;
       }
     }
+    bn = best_bn;
+    splitk = best_sk;
   }
-  if (splitk > 1) {
-    B200ST_CHECK(linear_epi && g.c_dtype == F32, "split-K needs a linear fp32 epilogue");
-    if (splitk > p.kb_total) splitk = p.kb_total;
-  }
+  if (splitk > p.kb_total) splitk = p.kb_total;
   p.kb_per_split = ceil_div(p.kb_total, splitk);
   splitk = ceil_div(p.kb_total, p.kb_per_split);   // no empty trailing split
   p.splitk = splitk;
   p.atomic = (splitk > 1) ? 1 : 0;
   p.dbg_trace = getenv("B200ST_DEBUG_TRACE_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("B200ST_DEBUG_TRACE_PTR"), nullptr, 0)) : nullptr;
-
-  // ---- BN selection: fewest waves x per-tile cycles.  Per k-block a CTA needs max(tensor time, L2->smem fill time):
-  // 4 MMAs of 128 x c x 16 take 2c cycles; the operand bytes (16 KB + 128c B) arrive at ~44 B/cycle/SM (measured:
-  // profiles/r01_gemm_shapes.md); the epilogue (~10 cycles per output column) overlaps the next tile's main loop.
-  int bn = dbg.force_bn;
-  if (bn == 0) {
-    double best = 1e30;
-    const int cands[3] = {256, 128, 64};
-    for (int c : cands) {
-      if (c > 64 && c >= 2 * ((g.N + 63) / 64 * 64)) continue;   // do not pad N by 2x or more
-      int64_t tiles = batch * p.m_tiles * ceil_div(g.N, c) * splitk;
-      int64_t waves = (tiles + num_sms - 1) / num_sms;
-      const double fill = (16384.0 + 128.0 * c) / 44.0, mma = 2.0 * c;
-      const double mainloop = p.kb_per_split * (fill > mma ? fill : mma);
-      const double epi = 10.0 * c + 600.0;
-      double cost = (double)waves * ((mainloop > epi ? mainloop : epi) + 800.0);
-      if (cost < best) { best = cost; bn = c; }
-    }
-  }
   p.n_tiles = ceil_div(g.N, bn);
   p.num_tiles = batch * p.m_tiles * p.n_tiles * splitk;
 
