@@ -667,7 +667,8 @@ static int speech_front_fwd(Ctx& c, const float* src, int B, int T, float* x0, F
   }
   GemmEpilogue ed = gemm_defaults().epi;
   B200ST_TRY(linear_fwd(c, sv.y2, (int64_t)F2 * C, B * T2, F2 * C, d, "src.dense.kernel", "src.dense.bias", ed, e0, F32, d));
-  RUN(posenc_fwd(e0, x0, B, T2, d, sqrtf((float)d), 0, c.drop(cf.postprocess_dropout, sv.s_in, (int64_t)B * T2 * d), c.st));
+  const DropoutSpec in_drop = c.drop(cf.postprocess_dropout, sv.s_in, (int64_t)B * T2 * d);   // outside RUN: allocates in the planning pass too
+  RUN(posenc_fwd(e0, x0, B, T2, d, sqrtf((float)d), 0, in_drop, c.st));
   return 0;
 }
 
@@ -853,7 +854,9 @@ static int run_planned(const Model& m, const Buffers& buf, cudaStream_t st, F&& 
   B200ST_TRY(body(real));
   B200ST_CHECK(!real.launch_failed, "dropout bitmap kernel launch failed");
   if (real.bits_pregenerated) {
-    B200ST_CHECK(real.drop_sites.size() == dry.drop_sites.size(), "dropout site plan mismatch");
+    B200ST_CHECK(real.drop_sites.size() == dry.drop_sites.size(),
+                 "dropout site plan mismatch: real " + std::to_string(real.drop_sites.size()) + " vs planned " +
+                     std::to_string(dry.drop_sites.size()));
     for (size_t i = 0; i < real.drop_sites.size(); ++i)
       B200ST_CHECK(real.drop_sites[i].arena_off == dry.drop_sites[i].arena_off && real.drop_sites[i].stream == dry.drop_sites[i].stream,
                    "dropout site plan mismatch");
