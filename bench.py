@@ -166,7 +166,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     lib.load()
     B, T, L, V = WORKLOAD["B"], WORKLOAD["T"], WORKLOAD["L"], WORKLOAD["V"]
     trainer, _ = build_speech_transformer_trainer(WORKLOAD["hparams"], V, precision="bf16", label_smoothing=0.1, seed=1234,
@@ -223,15 +224,14 @@ def run_gpu(args):
     ms_e2e = timed(e2e_step, args.steps)
 
     # roofline pass (not timed): per-launch CUDA events around the tcgen05 GEMM launches of ONE step
-    gemm = None
-    if rank == 0:
-        torch.cuda.synchronize()
-        lib.profile_begin()
-        trainer.use_cuda_graph = False          # eager launches so each GEMM can be bracketed by events
-        resident_step(0)
-        torch.cuda.synchronize()
-        gms, gfl, gn = lib.profile_end()
-        gemm = dict(ms=gms, flops=gfl, launches=gn)
+    # (every rank runs the same steps — train_step contains the gradient all-reduce — only rank 0 reports)
+    torch.cuda.synchronize()
+    lib.profile_begin()
+    trainer.use_cuda_graph = False          # eager launches so each GEMM can be bracketed by events
+    resident_step(0)
+    torch.cuda.synchronize()
+    gms, gfl, gn = lib.profile_end()
+    gemm = dict(ms=gms, flops=gfl, launches=gn)
     barrier()
     # kernels per step: counted on one eagerly launched step (a CUDA-graph replay re-issues the same kernel nodes)
     trainer.use_cuda_graph = False

@@ -9,6 +9,7 @@
 //           dQ tiles are reduced across kv blocks with fp32 vector RED into a scratch buffer.
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace b200st {
@@ -101,6 +102,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();      // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_trigger();
   const uint32_t tS = tmem;            // 128 columns
   const uint32_t tO = tmem + 128;      // 64 columns
 
@@ -305,6 +308,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();      // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_trigger();
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
 
   if (warp == 0) {
@@ -496,6 +501,8 @@ constexpr size_t kBwdSmem = 1024 + (size_t)(2 + 2 + 2 + 2 + 2) * kTile16K + 8 * 
 // dst(bf16)[r, 0..cols) = src(fp32)[r, 0..cols)   (dq scratch -> the q columns of the fused dqkv buffer)
 __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
                                  int64_t rows, int cols) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n8 = rows * (cols / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (cols / 8);
@@ -533,7 +540,7 @@ int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
     attr = true;
   }
   dim3 grid((Tq + BQ - 1) / BQ, H, B);
-  attn_fwd_kernel<<<grid, 320, kFwdSmem, s>>>(tq, tk, tv, p);
+  launch_pdl(attn_fwd_kernel, grid, 320, kFwdSmem, s, tq, tk, tv, p);
   tc_count_launch();
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -571,12 +578,12 @@ int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
   const int64_t rows = (int64_t)B * Tq;
   B200ST_CUDA(cudaMemsetAsync(dq_scratch, 0, sizeof(float) * (size_t)rows * H * DH, s));
   dim3 grid((Tk + BKV - 1) / BKV, H, B);
-  attn_bwd_kernel<<<grid, 320, kBwdSmem, s>>>(tq, tk, tv, tdo, p);
+  launch_pdl(attn_bwd_kernel, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
   B200ST_LAUNCH_CHECK();
   const int64_t n8 = rows * (H * DH / 8);
   int64_t g = (n8 + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  cast_rows_kernel<<<(int)g, 256, 0, s>>>(dq_scratch, (int64_t)H * DH, reinterpret_cast<__nv_bfloat16*>(dq), dq_ld, rows, H * DH);
+  launch_pdl(cast_rows_kernel, (int)g, 256, 0, s, dq_scratch, (int64_t)H * DH, reinterpret_cast<__nv_bfloat16*>(dq), dq_ld, rows, H * DH);
   tc_count_launch();
   g_kernel_launches += 1;
   B200ST_LAUNCH_CHECK();

@@ -2,14 +2,19 @@
 #include "../../include/b200st.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "pdl.cuh"
 #include "model.cuh"
 #include <cstring>
+#include <cstdlib>
+#include "pdl.cuh"
 #include <cmath>
 
 namespace b200st {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 int64_t g_kernel_launches = 0;
+cudaError_t& pdl_launch_error() { static thread_local cudaError_t e = cudaSuccess; return e; }
+bool pdl_enabled() { static const bool on = getenv("B200ST_NO_PDL") == nullptr; return on; }
 }  // namespace b200st
 
 using namespace b200st;
@@ -235,6 +240,8 @@ uint64_t b200st_dropout_stream_id(const char* site) { return site ? dropout_stre
 
 namespace b200st {
 __global__ void dropout_mask_kernel(uint64_t seed, uint64_t stream_id, int64_t n, float p, uint8_t* out) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = dropout_keep(seed, stream_id, (uint64_t)i, p) ? 1 : 0;
 }
@@ -245,7 +252,7 @@ extern "C" int b200st_dropout_mask(uint64_t seed, uint64_t stream_id, int64_t n,
   if (n == 0) return 0;
   int64_t g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  b200st::dropout_mask_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(seed, stream_id, n, p, out);
+  launch_pdl(b200st::dropout_mask_kernel, (int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream), seed, stream_id, n, p, out);
   B200ST_LAUNCH_CHECK();
   return 0;
 }

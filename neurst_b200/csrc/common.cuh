@@ -31,7 +31,16 @@ void set_last_error(const std::string& s);
     int _r = (expr);                                                                       \
     if (_r != 0) return _r;                                                                \
   } while (0)
-#define B200ST_LAUNCH_CHECK() B200ST_CUDA(cudaGetLastError())
+cudaError_t& pdl_launch_error();
+#define B200ST_LAUNCH_CHECK()                                                              \
+  do {                                                                                     \
+    if (::b200st::pdl_launch_error() != cudaSuccess) {                                     \
+      cudaError_t _pe = ::b200st::pdl_launch_error();                                      \
+      ::b200st::pdl_launch_error() = cudaSuccess;                                          \
+      B200ST_FAIL(std::string("kernel launch failed: ") + cudaGetErrorString(_pe));        \
+    }                                                                                      \
+    B200ST_CUDA(cudaGetLastError());                                                       \
+  } while (0)
 
 // ---- dtype helpers -----------------------------------------------------------------------
 template <typename T> struct DTypeOf;

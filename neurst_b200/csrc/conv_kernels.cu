@@ -8,6 +8,7 @@
 // of storing 164 M pre-activations) and the parameter-gradient partial sums.  conv1's filter gradient is then one
 // more split-K GEMM over the tiny im2col of the fbank (written by the same fused kernel).
 #include "kernels.cuh"
+#include "pdl.cuh"
 
 namespace b200st {
 
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 3 : 1)) conv1_fwd_kernel(cons
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, T* __restrict__ y, int B,
                                                          int Tn, int F, int Cin, int C, int T1, int F1, int use_ln) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float conv_smem[];
   const int lane = threadIdx.x & 31;
   ConvTaps<VEC, CPL, CIN1> taps;
@@ -207,6 +210,8 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 2 : 1)) conv1_bwd_fused_kerne
     const float* __restrict__ beta, float eps, const T* __restrict__ y1, const T* __restrict__ dcol, T* __restrict__ dz1,
     T* __restrict__ col1, int K1p, float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn,
     int F, int Cin, int C, int T1, int F1, int T2, int F2, int use_ln) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float conv_smem[];   // filter | bias | [3][C] block partials: db | dgamma | dbeta
   float* sacc = conv_smem + (9 * (CIN1 ? 1 : Cin) + 1) * (VEC ? ((C + 255) & ~255) : C);
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
@@ -307,6 +312,8 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 2 : 1)) conv1_bwd_fused_kerne
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ y1, T* __restrict__ col, int B, int T1, int F1,
                                                       int C, int T2, int F2) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t nchunks = (int64_t)B * T2 * F2 * 9;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -351,7 +358,7 @@ int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const fl
   const size_t smem = (size_t)(9 * Cin + 1) * ((C + 255) & ~255) * sizeof(float);
   B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
 #define FWD(VEC, CPL, CIN1)                                                                                             \
-  DISPATCH_DTYPE(y_dtype, TT, (conv1_fwd_kernel<TT, VEC, CPL, CIN1><<<grid, 256, smem, s>>>(src, w, b, gamma, beta, eps, (TT*)y1, \
+  DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_kernel<TT, VEC, CPL, CIN1>, grid, 256, smem, s, src, w, b, gamma, beta, eps, (TT*)y1, \
                                                                                         B, T, F, Cin, C, T1, F1, use_ln)))
   if (vec && C <= 256) { if (Cin == 1) FWD(true, 8, true); else FWD(true, 8, false); }
   else if (vec) { if (Cin == 1) FWD(true, 16, true); else FWD(true, 16, false); }
@@ -377,7 +384,7 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dz1) & 15) == 0);
 #define BWD(VEC, CPL, CIN1)                                                                                             \
-  DISPATCH_DTYPE(dtype, TT, (conv1_bwd_fused_kernel<TT, VEC, CPL, CIN1><<<grid, 256, smem, s>>>(                          \
+  DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_fused_kernel<TT, VEC, CPL, CIN1>, grid, 256, smem, s,                           \
       src, w, b, gamma, beta, eps, (const TT*)y1, (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, Cin, C, \
       T1, F1, T2, F2, use_ln)))
   if (vec && C <= 256) { if (Cin == 1) BWD(true, 8, true); else BWD(true, 8, false); }
@@ -397,8 +404,8 @@ int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, in
   const int grid = pick_grid(nchunks, 8, 148 * 16);
   const int esz = dtype == BF16 ? 2 : 4;
   const bool vec = ((C * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
-  if (vec) DISPATCH_DTYPE(dtype, TT, (im2col_kernel<TT, true><<<grid, 256, 0, s>>>((const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2)));
-  else DISPATCH_DTYPE(dtype, TT, (im2col_kernel<TT, false><<<grid, 256, 0, s>>>((const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2)));
+  if (vec) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2)));
+  else DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

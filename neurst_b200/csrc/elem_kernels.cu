@@ -1,6 +1,7 @@
 // LayerNorm / softmax / dropout-cast / reductions / positions / embedding / label-smoothed CE / Adam.
 // HBM-bound kernels: coalesced accesses along the feature axis, warp-shuffle reductions, fp32 math.
 #include "kernels.cuh"
+#include "pdl.cuh"
 #include <math.h>
 
 namespace b200st {
@@ -50,6 +51,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, c
                                                       const float* __restrict__ beta, float eps, TY* __restrict__ y,
                                                       float* __restrict__ y32, float* __restrict__ mean_out,
                                                       float* __restrict__ rstd_out, int64_t rows, int cols, int relu) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
@@ -81,6 +84,8 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const TX* __restrict__ 
                                                           const float* __restrict__ beta, float eps, TY* __restrict__ y,
                                                           float* __restrict__ y32, float* __restrict__ mean_out,
                                                           float* __restrict__ rstd_out, int64_t rows, int cols, int relu) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   float g[NV][4], bt[NV][4];
@@ -136,13 +141,13 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
                    ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!y32 || (reinterpret_cast<uintptr_t>(y32) & 15) == 0);
 #define LN_FWD_VEC(NV)                                                                                                  \
   DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,                                                               \
-      (ln_fwd_vec_kernel<TX, TY, NV><<<grid, 256, 0, s>>>((const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))))
+      (launch_pdl(ln_fwd_vec_kernel<TX, TY, NV>, grid, 256, 0, s, (const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))))
   if (vec && cols <= 256) LN_FWD_VEC(2);
   else if (vec && cols <= 512) LN_FWD_VEC(4);
   else if (vec) LN_FWD_VEC(8);
   else
     DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,
-        (ln_fwd_kernel<TX, TY><<<grid, 256, 0, s>>>((const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))));
+        (launch_pdl(ln_fwd_kernel<TX, TY>, grid, 256, 0, s, (const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))));
 #undef LN_FWD_VEC
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
@@ -159,6 +164,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                       const float* __restrict__ dres, TDX* __restrict__ dx,
                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
                                                       int cols, int relu) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];   // [2][cols] block partials
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
@@ -220,6 +227,8 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__
                                                           const float* __restrict__ dres, TDX* __restrict__ dx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
                                                           int cols, int relu) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];   // [2][cols] block partials
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
@@ -293,14 +302,14 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
   const size_t smem = 2 * (size_t)cols * sizeof(float);
 #define LN_BWD_LAUNCH(CPL)                                                                                              \
   DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
-      (ln_bwd_kernel<TDY, TX, TDX, CPL><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
+      (launch_pdl(ln_bwd_kernel<TDY, TX, TDX, CPL>, grid, 256, smem, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
                                                                 (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
   const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0);
 #define LN_BWD_VEC(NV)                                                                                                  \
   DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
-      (ln_bwd_vec_kernel<TDY, TX, TDX, NV><<<grid, 256, smem, s>>>((const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
+      (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV>, grid, 256, smem, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
                                                                    (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
   if (vec && cols <= 256) LN_BWD_VEC(2);
   else if (vec && cols <= 512) LN_BWD_VEC(4);
@@ -359,6 +368,8 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
                                                            const float* __restrict__ bias, int causal,
                                                            T* __restrict__ P_pre, T* __restrict__ P_drop, int64_t ldP,
                                                            int B, int H, int Tq, int Tk, DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * Tq;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -426,7 +437,7 @@ int softmax_fwd(const float* S, int64_t ldS, const float* bias, int causal, void
   B200ST_CHECK((reinterpret_cast<uintptr_t>(S) & 31) == 0 && (reinterpret_cast<uintptr_t>(P_pre) & 15) == 0, "softmax alignment");
   B200ST_CHECK(Tk <= 2048, "softmax supports up to 2048 keys");
   const int grid = grid_for(rows, 8);
-#define SM_FWD(ST) DISPATCH_DTYPE(p_dtype, T, (softmax_fwd_kernel<T, ST><<<grid, 256, 0, s>>>(S, ldS, bias, causal, (T*)P_pre, \
+#define SM_FWD(ST) DISPATCH_DTYPE(p_dtype, T, (launch_pdl(softmax_fwd_kernel<T, ST>, grid, 256, 0, s, S, ldS, bias, causal, (T*)P_pre, \
                                                                                    (T*)P_drop, ldP, B, H, Tq, Tk, drop)))
   if (Tk <= 256) SM_FWD(1); else if (Tk <= 512) SM_FWD(2); else if (Tk <= 1024) SM_FWD(4); else SM_FWD(8);
 #undef SM_FWD
@@ -439,6 +450,8 @@ template <typename T, int STEPS>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ dP, int64_t ldS,
                                                            const T* __restrict__ P_pre, T* __restrict__ dS, int64_t ldP,
                                                            int64_t rows, int Tk, DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const uint32_t thresh = dropout_thresh16(drop.p);
@@ -480,7 +493,7 @@ int softmax_bwd(const float* dP, int64_t ldS, const void* P_pre, void* dS, int p
   if (rows == 0) return 0;
   B200ST_CHECK(ldS % 8 == 0 && ldP % 8 == 0 && Tk <= 2048, "softmax_bwd needs row strides padded to 8 and Tk <= 2048");
   const int grid = grid_for(rows, 8);
-#define SM_BWD(ST) DISPATCH_DTYPE(p_dtype, T, (softmax_bwd_kernel<T, ST><<<grid, 256, 0, s>>>(dP, ldS, (const T*)P_pre, (T*)dS, \
+#define SM_BWD(ST) DISPATCH_DTYPE(p_dtype, T, (launch_pdl(softmax_bwd_kernel<T, ST>, grid, 256, 0, s, dP, ldS, (const T*)P_pre, (T*)dS, \
                                                                                    ldP, rows, Tk, drop)))
   if (Tk <= 256) SM_BWD(1); else if (Tk <= 512) SM_BWD(2); else if (Tk <= 1024) SM_BWD(4); else SM_BWD(8);
 #undef SM_BWD
@@ -495,6 +508,8 @@ int softmax_bwd(const float* dP, int64_t ldS, const void* P_pre, void* dS, int p
 template <typename T>
 __global__ void __launch_bounds__(256) cast_dropout_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n,
                                                            DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t thresh = dropout_thresh16(drop.p);
   const int64_t ngroups = (n + 7) / 8;
   const bool vec = (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 31) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
@@ -514,7 +529,7 @@ __global__ void __launch_bounds__(256) cast_dropout_kernel(const float* __restri
 }
 int cast_dropout(const float* x, void* y, int y_dtype, int64_t n, DropoutSpec drop, cudaStream_t s) {
   if (n == 0) return 0;
-  DISPATCH_DTYPE(y_dtype, T, (cast_dropout_kernel<T><<<grid_for((n + 7) / 8, 256), 256, 0, s>>>(x, (T*)y, n, drop)));
+  DISPATCH_DTYPE(y_dtype, T, (launch_pdl(cast_dropout_kernel<T>, grid_for((n + 7) / 8, 256), 256, 0, s, x, (T*)y, n, drop)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -525,6 +540,8 @@ int cast_dropout(const float* x, void* y, int y_dtype, int64_t n, DropoutSpec dr
 // (block, column).
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dY, int64_t M, int N, int64_t ld, float* __restrict__ db) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n0 = blockIdx.x * 256 + lane * 8;
@@ -554,6 +571,8 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ d
 
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dY, int64_t M, int N, int64_t ld, float* __restrict__ db) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -578,14 +597,14 @@ int colsum_accum(const void* dY, int dtype, int64_t M, int N, int64_t ld, float*
     const int cap = (148 * 4 + gx - 1) / gx;
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
-    DISPATCH_DTYPE(dtype, T, (colsum_vec_kernel<T><<<dim3(gx, gy), 256, 0, s>>>((const T*)dY, M, N, ld, db)));
+    DISPATCH_DTYPE(dtype, T, (launch_pdl(colsum_vec_kernel<T>, dim3(gx, gy), 256, 0, s, (const T*)dY, M, N, ld, db)));
   } else {
     dim3 block(32, 8);
     int gy = (int)((M + 255) / 256);
     if (gy > 64) gy = 64;
     if (gy < 1) gy = 1;
     dim3 grid(ceil_div(N, 32), gy);
-    DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, block, 0, s>>>((const T*)dY, M, N, ld, db)));
+    DISPATCH_DTYPE(dtype, T, (launch_pdl(colsum_kernel<T>, grid, block, 0, s, (const T*)dY, M, N, ld, db)));
   }
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
@@ -604,6 +623,8 @@ __device__ __forceinline__ float sinusoid(int t, int c, int d) {
 
 __global__ void posenc_fwd_kernel(const float* __restrict__ v, float* __restrict__ x, int B, int T, int d, float scale,
                                   int t0, DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = (int64_t)B * T * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -616,7 +637,7 @@ __global__ void posenc_fwd_kernel(const float* __restrict__ v, float* __restrict
 int posenc_fwd(const float* v, float* x, int B, int T, int d, float scale, int t0, DropoutSpec drop, cudaStream_t s) {
   const int64_t n = (int64_t)B * T * d;
   if (n == 0) return 0;
-  posenc_fwd_kernel<<<grid_for(n, 256 * 2), 256, 0, s>>>(v, x, B, T, d, scale, t0, drop);
+  launch_pdl(posenc_fwd_kernel, grid_for(n, 256 * 2), 256, 0, s, v, x, B, T, d, scale, t0, drop);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -624,6 +645,8 @@ int posenc_fwd(const float* v, float* x, int B, int T, int d, float scale, int t
 
 template <typename T>
 __global__ void posenc_bwd_kernel(const float* __restrict__ dx, T* __restrict__ dv, int64_t n, float scale, DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float g = dx[i];
     if (drop.p > 0.f) g = drop_keep1(drop, (uint64_t)i) ? g * drop.scale : 0.f;
@@ -632,7 +655,7 @@ __global__ void posenc_bwd_kernel(const float* __restrict__ dx, T* __restrict__ 
 }
 int posenc_bwd(const float* dx, void* dv, int dv_dtype, int64_t n, float scale, DropoutSpec drop, cudaStream_t s) {
   if (n == 0) return 0;
-  DISPATCH_DTYPE(dv_dtype, T, (posenc_bwd_kernel<T><<<grid_for(n, 256 * 4), 256, 0, s>>>(dx, (T*)dv, n, scale, drop)));
+  DISPATCH_DTYPE(dv_dtype, T, (launch_pdl(posenc_bwd_kernel<T>, grid_for(n, 256 * 4), 256, 0, s, dx, (T*)dv, n, scale, drop)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -640,6 +663,8 @@ int posenc_bwd(const float* dx, void* dv, int dv_dtype, int64_t n, float scale, 
 
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ E, float* __restrict__ x, int B,
                                  int L, int d, int V, int t0, float scale, DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = (int64_t)B * L * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -656,13 +681,15 @@ int embed_fwd(const int64_t* ids, const float* E, float* x, int B, int L, int d,
               cudaStream_t s) {
   const int64_t n = (int64_t)B * L * d;
   if (n == 0) return 0;
-  embed_fwd_kernel<<<grid_for(n, 256 * 2), 256, 0, s>>>(ids, E, x, B, L, d, V, t0, sqrtf((float)d), drop);
+  launch_pdl(embed_fwd_kernel, grid_for(n, 256 * 2), 256, 0, s, ids, E, x, B, L, d, V, t0, sqrtf((float)d), drop);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dE,
                                  int B, int L, int d, int V, float scale, DropoutSpec drop) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = (int64_t)B * L * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -677,13 +704,15 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const float* _
 int embed_bwd(const int64_t* ids, const float* dx, float* dE, int B, int L, int d, int V, DropoutSpec drop, cudaStream_t s) {
   const int64_t n = (int64_t)B * L * d;
   if (n == 0) return 0;
-  embed_bwd_kernel<<<grid_for(n, 256 * 2), 256, 0, s>>>(ids, dx, dE, B, L, d, V, sqrtf((float)d), drop);
+  launch_pdl(embed_bwd_kernel, grid_for(n, 256 * 2), 256, 0, s, ids, dx, dE, B, L, d, V, sqrtf((float)d), drop);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void length_to_bias_kernel(const int64_t* __restrict__ lengths, float* __restrict__ bias, int B, int T, int n_halvings) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = (int64_t)B * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / T), t = (int)(i % T);
@@ -694,18 +723,20 @@ __global__ void length_to_bias_kernel(const int64_t* __restrict__ lengths, float
 }
 int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s) {
   if ((int64_t)B * T == 0) return 0;
-  length_to_bias_kernel<<<grid_for((int64_t)B * T, 256), 256, 0, s>>>(lengths, bias, B, T, n_halvings);
+  launch_pdl(length_to_bias_kernel, grid_for((int64_t)B * T, 256), 256, 0, s, lengths, bias, B, T, n_halvings);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 __global__ void padding_to_bias_kernel(const float* __restrict__ padding, float* __restrict__ bias, int64_t n) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     bias[i] = padding[i] * kFloatMin;
 }
 int padding_to_bias(const float* padding, float* bias, int64_t n, cudaStream_t s) {
   if (n == 0) return 0;
-  padding_to_bias_kernel<<<grid_for(n, 256), 256, 0, s>>>(padding, bias, n);
+  launch_pdl(padding_to_bias_kernel, grid_for(n, 256), 256, 0, s, padding, bias, n);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -734,6 +765,8 @@ __global__ void __launch_bounds__(256) lsce_kernel(const float* __restrict__ log
                                                     const int64_t* __restrict__ trg_length, int B, int L, int V,
                                                     float eps_ls, float* __restrict__ nll_sum, T* __restrict__ dlogits,
                                                     float loss_scale) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sm[32];
   const int64_t row = blockIdx.x;
   const int b = (int)(row / L), l = (int)(row % L);
@@ -774,6 +807,8 @@ __global__ void __launch_bounds__(256) lsce_kernel(const float* __restrict__ log
 
 __global__ void lsce_finalize_kernel(const float* __restrict__ nll_sum, const int64_t* __restrict__ trg_length, int B, int L,
                                      float* __restrict__ n_tokens, float* __restrict__ loss) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sm[32];
   float a = 0.f, t = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
@@ -792,10 +827,10 @@ int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_len
                  float loss_scale, cudaStream_t s) {
   if (B * L == 0) return 0;
   B200ST_CUDA(cudaMemsetAsync(nll_sum, 0, sizeof(float) * B, s));
-  DISPATCH_DTYPE(d_dtype, T, (lsce_kernel<T><<<B * L, 256, 0, s>>>(logits, trg, trg_length, B, L, V, label_smoothing, nll_sum,
+  DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_kernel<T>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing, nll_sum,
                                                                     (T*)dlogits, loss_scale)));
   B200ST_LAUNCH_CHECK();
-  lsce_finalize_kernel<<<1, 256, 0, s>>>(nll_sum, trg_length, B, L, n_tokens, loss);
+  launch_pdl(lsce_finalize_kernel, 1, 256, 0, s, nll_sum, trg_length, B, L, n_tokens, loss);
   g_kernel_launches += 2;
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -807,6 +842,8 @@ int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_len
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, float b1, float b2, float eps,
                             float gscale, int zero_grad) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -820,12 +857,14 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
 int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
               float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s) {
   if (n == 0) return 0;
-  adam_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
+  launch_pdl(adam_kernel, grid_for(n, 256 * 4), 256, 0, s, p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 __global__ void dropout_bits_kernel(DropoutSpec drop, int64_t ngroups, uint8_t* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t thresh = dropout_thresh16(drop.p);
   const uint64_t seed = dropout_seed(drop);
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x)
@@ -834,13 +873,15 @@ __global__ void dropout_bits_kernel(DropoutSpec drop, int64_t ngroups, uint8_t* 
 int dropout_bits(DropoutSpec drop, int64_t n_elems, uint8_t* out, cudaStream_t s) {
   const int64_t ng = (n_elems + 7) / 8;
   if (ng == 0) return 0;
-  dropout_bits_kernel<<<grid_for(ng, 256), 256, 0, s>>>(drop, ng, out);
+  launch_pdl(dropout_bits_kernel, grid_for(ng, 256), 256, 0, s, drop, ng, out);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 __global__ void __launch_bounds__(256) dropout_bits_multi_kernel(const DropBitsTable t, uint64_t seed, const uint64_t* seed_ptr,
                                                                   uint8_t* __restrict__ base) {
+  pdl_wait();
+  pdl_trigger();
   const uint64_t sd = seed_ptr ? *seed_ptr : seed;
   const int64_t total = t.goff[t.n];
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
@@ -852,28 +893,32 @@ __global__ void __launch_bounds__(256) dropout_bits_multi_kernel(const DropBitsT
 }
 int dropout_bits_multi(const DropBitsTable& t, uint64_t seed, const uint64_t* seed_ptr, uint8_t* base, cudaStream_t s) {
   if (t.n == 0 || t.goff[t.n] == 0) return 0;
-  dropout_bits_multi_kernel<<<grid_for(t.goff[t.n], 256, 148 * 8), 256, 0, s>>>(t, seed, seed_ptr, base);
+  launch_pdl(dropout_bits_multi_kernel, grid_for(t.goff[t.n], 256, 148 * 8), 256, 0, s, t, seed, seed_ptr, base);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
 }
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s) {
   if (n == 0) return 0;
-  cast_bf16_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, y, n);
+  launch_pdl(cast_bf16_kernel, grid_for(n, 256 * 4), 256, 0, s, x, y, n);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
 }
 __global__ void fill_kernel(float* __restrict__ x, float v, int64_t n) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
 }
 int fill_f32(float* x, float v, int64_t n, cudaStream_t s) {
   if (n == 0) return 0;
-  fill_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(x, v, n);
+  launch_pdl(fill_kernel, grid_for(n, 256 * 4), 256, 0, s, x, v, n);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

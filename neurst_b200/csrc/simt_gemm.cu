@@ -5,6 +5,7 @@
 // (d = 4..16, which no tensor-core tile fits) — and (b) as the on-device cross-check of the tcgen05 kernel.
 // Operands may be fp32 or bf16 in memory; accumulation is always fp32.
 #include "gemm.cuh"
+#include "pdl.cuh"
 
 namespace b200st {
 namespace {
@@ -12,6 +13,8 @@ namespace {
 constexpr int TM = 64, TN = 64, TK = 16;
 
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmArgs g) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
   const int b = blockIdx.z;
@@ -79,7 +82,7 @@ int gemm_simt_f32(const GemmArgs& g, cudaStream_t stream) {
   const int64_t nb = (int64_t)g.nb1 * g.nb2;
   B200ST_CHECK(nb <= 65535 && ceil_div(g.M, TM) <= 65535, "grid too large for SIMT GEMM");
   dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM), (unsigned)nb);
-  simt_gemm_kernel<<<grid, 256, 0, stream>>>(g);
+  launch_pdl(simt_gemm_kernel, grid, 256, 0, stream, g);
   B200ST_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,7 @@
 // Replaces the cuBLAS calls behind tf.einsum / Dense / Conv2D at the reference sites listed in
 // SURVEY.md §2.3 (K3,K4,K8,K9,K10,K11,K13,K15), e.g. neurst/layers/common_layers.py:270,276-288.
 #include "gemm.cuh"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
@@ -220,6 +221,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();      // everything above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -521,7 +524,7 @@ int launch_out(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
     B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(ta, tb, tc, p);
+  launch_pdl(kern, grid, kThreads, smem, stream, ta, tb, tc, p);
   B200ST_LAUNCH_CHECK();
   return 0;
 }
