@@ -64,34 +64,61 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // ==============================================================================================================
 // forward: 320 threads = TMA warp + MMA warp + 8 softmax warps (2 per TMEM lane quadrant, each owning 64 of the 128
-// key columns of a block); ~84 KB smem and 256 TMEM columns so that two CTAs share an SM.
+// key columns of a block); ~100 KB smem and 256 TMEM columns so that two CTAs share an SM.  K is double-buffered (the
+// next S = QK^T is issued right behind PV), V single-buffered (only needed after the next softmax).
+// Element math is branch-free: the key bias (times log2 e, -inf beyond Tk) sits in a shared-memory table read with
+// broadcast LDS.128, the logit is one FFMA, exp is one MUFU.EX2, the dropout scale is folded into the final 1/l.
 // ==============================================================================================================
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 64 keep-bits (keys k0 .. k0+63 of one query row) from the precomputed bitmap or regenerated; bits of keys >= Tkp read as 1
+__device__ __forceinline__ void load_keep64(const DropoutSpec& d, bool row_ok, int64_t row_bit0, int k0, int Tkp, uint32_t thresh,
+                                            uint32_t (&keep)[2]) {
+  keep[0] = keep[1] = 0xffffffffu;
+  if (!(d.p > 0.f) || !row_ok) return;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (k0 + 8 * g < Tkp) {
+      const uint32_t byte = drop_keep8(d, (uint64_t)(row_bit0 + k0 + 8 * g) >> 3, thresh);
+      keep[g >> 2] = (keep[g >> 2] & ~(0xffu << (8 * (g & 3)))) | (byte << (8 * (g & 3)));
+    }
+  }
+}
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(320, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nblk = (p.Tk + BKV - 1) / BKV;
   const uint32_t sQ = base;                          // 16 KB
-  const uint32_t sK = sQ + kTile16K;                 // 16 KB
-  const uint32_t sV = sK + kTile16K;                 // 16 KB
+  const uint32_t sK = sQ + kTile16K;                 // 2 x 16 KB
+  const uint32_t sV = sK + 2 * kTile16K;             // 16 KB
   const uint32_t sP = sV + kTile16K;                 // 32 KB
   const uint32_t sX = sP + 2 * kTile16K;             // exchange: max [2][2][128] + sum [2][128] floats = 3 KB
-  const uint32_t bars = sX + 3072;
-  const uint32_t q_full = bars, kv_full = bars + 8, kv_empty = bars + 16, s_full = bars + 24, s_empty = bars + 32,
+  const uint32_t sB = sX + 3072;                     // key bias * log2(e), [nblk * 128] floats
+  const uint32_t bars = sB + (uint32_t)nblk * 512u;
+  const uint32_t q_full = bars, v_full = bars + 8, v_empty = bars + 16, s_full = bars + 24, s_empty = bars + 32,
                  p_full = bars + 40, p_empty = bars + 48, o_ready = bars + 56, tmem_slot = bars + 64;
+  auto k_full = [&](int s2) { return bars + 72u + 8u * s2; };
+  auto k_empty = [&](int s2) { return bars + 88u + 8u * s2; };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
   float* xch = reinterpret_cast<float*>(smem_raw + (sX - ptx::smem_u32(smem_raw)));
+  float* btab = reinterpret_cast<float*>(smem_raw + (sB - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.Tk + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
     ptx::mbar_init(q_full, 1);
-    ptx::mbar_init(kv_full, 1); ptx::mbar_init(kv_empty, 1);
+    ptx::mbar_init(v_full, 1); ptx::mbar_init(v_empty, 1);
+    for (int s2 = 0; s2 < 2; ++s2) { ptx::mbar_init(k_full(s2), 1); ptx::mbar_init(k_empty(s2), 1); }
     ptx::mbar_init(s_full, 1); ptx::mbar_init(s_empty, 8);
     ptx::mbar_init(p_full, 8); ptx::mbar_init(p_empty, 1);
     ptx::mbar_init(o_ready, 1);
@@ -112,10 +139,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_arrive_expect_tx(q_full, kTile16K);
       ptx::tma_load_4d(sQ, &tmQ, q_full, 0, qt * BQ, h, b);
       for (int j = 0; j < nblk; ++j) {
-        ptx::mbar_wait(kv_empty, ((uint32_t)j & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(kv_full, 2 * kTile16K);
-        ptx::tma_load_4d(sK, &tmK, kv_full, 0, j * BKV, h, b);
-        ptx::tma_load_4d(sV, &tmV, kv_full, 0, j * BKV, h, b);
+        const int s2 = j & 1;
+        ptx::mbar_wait(k_empty(s2), (((uint32_t)j >> 1) & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(k_full(s2), kTile16K);
+        ptx::tma_load_4d(sK + s2 * kTile16K, &tmK, k_full(s2), 0, j * BKV, h, b);
+        ptx::mbar_wait(v_empty, ((uint32_t)j & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(v_full, kTile16K);
+        ptx::tma_load_4d(sV, &tmV, v_full, 0, j * BKV, h, b);
       }
     }
   } else if (warp == 1) {
@@ -125,21 +155,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_wait(q_full, 0);
       for (int j = 0; j < nblk; ++j) {
         const uint32_t ph = (uint32_t)j & 1u;
-        ptx::mbar_wait(kv_full, ph);
+        const uint32_t k_s = sK + (uint32_t)(j & 1) * kTile16K;
+        ptx::mbar_wait(k_full(j & 1), ((uint32_t)j >> 1) & 1u);
         ptx::mbar_wait(s_empty, ph ^ 1u);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          ptx::mma_f16_ss(tS, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sK + k * 32, 16, 1024),
+          ptx::mma_f16_ss(tS, ptx::make_smem_desc_sw128(sQ + k * 32, 16, 1024), ptx::make_smem_desc_sw128(k_s + k * 32, 16, 1024),
                           idesc_s, k > 0 ? 1u : 0u);
         ptx::mma_commit(s_full);
+        ptx::mma_commit(k_empty(j & 1));
+        ptx::mbar_wait(v_full, ph);
         ptx::mbar_wait(p_full, ph);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
           ptx::mma_f16_ss(tO, ptx::make_smem_desc_sw128(sP + (k >> 2) * kTile16K + (k & 3) * 32, 16, 1024),
                           ptx::make_smem_desc_sw128(sV + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        ptx::mma_commit(kv_empty);
+        ptx::mma_commit(v_empty);
         ptx::mma_commit(p_empty);
         ptx::mma_commit(o_ready);
       }
@@ -151,105 +184,114 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = quad * 32 + lane;
     const int q = qt * BQ + row;
     const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
-    const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t thresh = dropout_thresh16(p.drop.p);
+    const float a2 = p.alpha * kLog2e;
+    const int qlim = q + (p.Tk - p.Tq);               // causal: keys k > qlim get the additive FLOAT_MIN
+    const float cmask = kMaskMin * kLog2e;
+    {
+      const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
+      for (int k = threadIdx.x - 64; k < nblk * BKV; k += 256)
+        btab[k] = (k < p.Tk) ? (bias_row ? __ldg(bias_row + k) * kLog2e : 0.f) : -INFINITY;
+      softmax_bar();
+    }
     float m = -INFINITY, l = 0.f;      // running row max (log2 domain, shared by both halves) and this half's partial sum
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
+      const int kbase = j * BKV + half * 64;          // first key of this thread's 64 columns
+      uint32_t keep[2];
+      load_keep64(p.drop, q < p.Tq, row_g * p.Tkp, kbase, p.Tkp, thresh, keep);
       ptx::mbar_wait(s_full, ph);
       ptx::tc_fence_after();
-      // pass 1: maximum over this half's 64 columns, then exchange with the partner warp
-      float bmax = -INFINITY;
-#pragma unroll 1
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-        uint32_t r[32];
+      // logits (log2 domain) of this thread's 64 columns, kept in registers
+      uint32_t r[64];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, r);
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + half * 64, r0);
+        ptx::tmem_ld_32x32b_x32(tS + lane_addr + half * 64 + 32, r1);
         ptx::tmem_ld_wait();
+      }
+      float bmax = -INFINITY;
+      const float4* bt4 = reinterpret_cast<const float4*>(btab + kbase);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = j * BKV + c0 + i;
-          if (k < p.Tk) bmax = fmaxf(bmax, logit(p, __uint_as_float(r[i]), bias_row, k, q) * kLog2e);
+      for (int i4 = 0; i4 < 16; ++i4) {
+        const float4 bb = bt4[i4];
+        float x0 = fmaf(__uint_as_float(r[4 * i4 + 0]), a2, bb.x), x1 = fmaf(__uint_as_float(r[4 * i4 + 1]), a2, bb.y);
+        float x2 = fmaf(__uint_as_float(r[4 * i4 + 2]), a2, bb.z), x3 = fmaf(__uint_as_float(r[4 * i4 + 3]), a2, bb.w);
+        if (CAUSAL) {
+          const int k = kbase + 4 * i4;
+          x0 = (k + 0 > qlim) ? x0 + cmask : x0; x1 = (k + 1 > qlim) ? x1 + cmask : x1;
+          x2 = (k + 2 > qlim) ? x2 + cmask : x2; x3 = (k + 3 > qlim) ? x3 + cmask : x3;
         }
+        r[4 * i4 + 0] = __float_as_uint(x0); r[4 * i4 + 1] = __float_as_uint(x1);
+        r[4 * i4 + 2] = __float_as_uint(x2); r[4 * i4 + 3] = __float_as_uint(x3);
+        bmax = fmaxf(fmaxf(bmax, fmaxf(x0, x1)), fmaxf(x2, x3));
       }
       xch[(ph * 2 + half) * 128 + row] = bmax;
       softmax_bar();
       bmax = fmaxf(bmax, xch[(ph * 2 + (half ^ 1)) * 128 + row]);
       const float m_new = fmaxf(m, bmax);
-      const float corr = exp2f(m - m_new);           // 0 on the first block (m = -inf)
-      // rescale this half's 32 output columns once the previous PV product has landed
-      if (j > 0) {
-        ptx::mbar_wait(o_ready, ph ^ 1u);
-        ptx::tc_fence_after();
-        uint32_t r[32];
-        __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tO + lane_addr + half * 32, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
-        ptx::tmem_st_32x32b_x32(tO + lane_addr + half * 32, r);
-        ptx::tmem_st_wait();
-      }
-      // pass 2: probabilities -> bf16 P tile in shared memory (A operand of the PV product)
+      const float corr = ex2_approx(m - m_new);       // 0 on the first block (m = -inf)
+      // probabilities -> bf16 P tile in shared memory (A operand of the PV product); dropout scale applied at the end
       ptx::mbar_wait(p_empty, ph ^ 1u);
       float bsum = 0.f;
-#pragma unroll 1
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-        uint32_t r[32];
-        __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, r);
-        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int k0 = j * BKV + c0 + g8 * 8;
-          float pv[8];
+      for (int g8 = 0; g8 < 8; ++g8) {
+        const uint32_t kb = keep[g8 >> 2] >> (8 * (g8 & 3));
+        float pv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = k0 + i;
-            float pr = 0.f;
-            if (k < p.Tk) pr = exp2f(logit(p, __uint_as_float(r[g8 * 8 + i]), bias_row, k, q) * kLog2e - m_new);
-            bsum += pr;
-            pv[i] = pr;
-          }
-          if (p.drop.p > 0.f) {
-            const uint32_t keep = drop_keep8(p.drop, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = ((keep >> i) & 1u) ? pv[i] * p.drop.scale : 0.f;
-          }
-          st_shared_v4(sP + swz_off(row, c0 + g8 * 8), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
-                       pack_bf16(pv[6], pv[7]));
+        for (int i = 0; i < 8; ++i) {
+          const float pr = ex2_approx(__uint_as_float(r[g8 * 8 + i]) - m_new);
+          bsum += pr;
+          pv[i] = ((kb >> i) & 1u) ? pr : 0.f;
         }
+        st_shared_v4(sP + swz_off(row, half * 64 + g8 * 8), pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                     pack_bf16(pv[6], pv[7]));
       }
       l = l * corr + bsum;
       m = m_new;
+      // rescale this half's 32 output columns (after the logits registers are dead) once the previous PV product has landed
+      if (j > 0) {
+        ptx::mbar_wait(o_ready, ph ^ 1u);
+        ptx::tc_fence_after();
+        uint32_t ro[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tO + lane_addr + half * 32, ro);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * corr);
+        ptx::tmem_st_32x32b_x32(tO + lane_addr + half * 32, ro);
+        ptx::tmem_st_wait();
+      }
       ptx::fence_proxy_async_smem();       // P (generic-proxy writes) -> visible to the tensor-core (async) proxy
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) { ptx::mbar_arrive(s_empty); ptx::mbar_arrive(p_full); }
     }
-    // ---- epilogue: O / l -> ctx, LSE ----
+    // ---- epilogue: O * scale / l -> ctx, LSE ----
     float* xsum = xch + 512;
     xsum[half * 128 + row] = l;
     softmax_bar();
     l += xsum[(half ^ 1) * 128 + row];
     ptx::mbar_wait(o_ready, (uint32_t)(nblk - 1) & 1u);
     ptx::tc_fence_after();
-    const float inv_l = 1.0f / l;
+    const float inv_l = ((p.drop.p > 0.f) ? p.drop.scale : 1.0f) / l;
     __nv_bfloat16* dst = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH + half * 32;
     {
-      uint32_t r[32];
+      uint32_t ro[32];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(tO + lane_addr + half * 32, r);
+      ptx::tmem_ld_32x32b_x32(tO + lane_addr + half * 32, ro);
       ptx::tmem_ld_wait();
       if (q < p.Tq) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-          pk.y = pack_bf16(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-          pk.z = pack_bf16(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-          pk.w = pack_bf16(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
+          pk.x = pack_bf16(__uint_as_float(ro[i]) * inv_l, __uint_as_float(ro[i + 1]) * inv_l);
+          pk.y = pack_bf16(__uint_as_float(ro[i + 2]) * inv_l, __uint_as_float(ro[i + 3]) * inv_l);
+          pk.z = pack_bf16(__uint_as_float(ro[i + 4]) * inv_l, __uint_as_float(ro[i + 5]) * inv_l);
+          pk.w = pack_bf16(__uint_as_float(ro[i + 6]) * inv_l, __uint_as_float(ro[i + 7]) * inv_l);
           *reinterpret_cast<uint4*>(dst + i) = pk;
         }
       }
@@ -269,6 +311,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnParams p) {
@@ -289,7 +332,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t dq_full = bars + 8u * 7;
   const uint32_t dq_empty = bars + 8u * 8;
   const uint32_t tmem_slot = bars + 8u * 9;
+  const uint32_t sB = bars + 128;                    // key bias * log2(e) of this kv block, 128 floats
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+  float* btab = reinterpret_cast<float*>(smem_raw + (sB - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -371,67 +416,84 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // 8 compute warps: thread = (row of the tile, half of the columns); no cross-warp reductions are needed in backward
+    // 8 compute warps: thread = (row of the tile, half of the columns); no cross-warp reductions are needed in backward.
+    // Branch-free element math as in the forward kernel (bias table in smem, one FFMA + one MUFU per probability); the
+    // dropout scale is folded into dS (FFMA) and into the dV epilogue.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
     const uint32_t thresh = dropout_thresh16(p.drop.p);
+    const float a2 = p.alpha * kLog2e;
+    const float cmask = kMaskMin * kLog2e;
+    const float dscale = (p.drop.p > 0.f) ? p.drop.scale : 1.0f;
+    {
+      const float* bias_row = p.bias ? p.bias + (int64_t)b * p.Tk : nullptr;
+      const int t = threadIdx.x - 64;
+      if (t < BKV) {
+        const int k = jb * BKV + t;
+        btab[t] = (k < p.Tk) ? (bias_row ? __ldg(bias_row + k) * kLog2e : 0.f) : -INFINITY;
+      }
+      softmax_bar();
+    }
+    const int kbase = jb * BKV + half * 64;
+    const float4* bt4 = reinterpret_cast<const float4*>(btab + half * 64);
     for (int i = 0; i < nq; ++i) {
       const int q = i * BQ + row;
       const bool qv = q < p.Tq;
       const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
-      // D = rowsum(dO * O), LSE (log2 domain)
-      float Dq = 0.f, lse2 = 0.f;
+      const int qlim = q + (p.Tk - p.Tq);
+      uint32_t keep[2];
+      load_keep64(p.drop, qv, row_g * p.Tkp, kbase, p.Tkp, thresh, keep);
+      // D = rowsum(dO * O), LSE (log2 domain; +inf on padding rows => P = 0)
+      float Dq = 0.f, lse2 = INFINITY;
       if (qv) {
         const __nv_bfloat16* o_row = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH;
         const __nv_bfloat16* do_row = p.dctx + ((int64_t)b * p.Tq + q) * p.dctx_ld + h * DH;
+        uint4 av[8], dv4[8];
 #pragma unroll
-        for (int c = 0; c < DH; c += 8) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(o_row + c)), d = __ldg(reinterpret_cast<const uint4*>(do_row + c));
-          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+        for (int c = 0; c < 8; ++c) {
+          av[c] = __ldg(reinterpret_cast<const uint4*>(o_row + 8 * c));
+          dv4[c] = __ldg(reinterpret_cast<const uint4*>(do_row + 8 * c));
+        }
+        lse2 = p.lse[row_g] * kLog2e;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&av[c]);
+          const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dv4[c]);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 x = __bfloat1622float2(ah[t]), y = __bfloat1622float2(dh[t]);
-            Dq += x.x * y.x + x.y * y.y;
+            Dq = fmaf(x.x, y.x, fmaf(x.y, y.y, Dq));
           }
         }
-        lse2 = p.lse[row_g] * kLog2e;
       }
       ptx::mbar_wait(sdp_full, (uint32_t)i & 1u);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
         uint32_t rs[32], rp[32];
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
         ptx::tmem_ld_32x32b_x32(tdP + lane_addr + c0, rp);
         ptx::tmem_ld_wait();
+        const uint32_t kw = keep[cc];
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const int k0 = jb * BKV + c0 + g8 * 8;
-          uint32_t keep = 0xffu;
-          if (p.drop.p > 0.f) keep = drop_keep8(p.drop, (uint64_t)(row_g * p.Tkp + k0) >> 3, thresh);
+          const float4 b0 = bt4[cc * 8 + g8 * 2], b1 = bt4[cc * 8 + g8 * 2 + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const uint32_t kb = kw >> (8 * g8);
           float pd[8], ds[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const int k = k0 + t;
-            float pr = 0.f, dsv = 0.f, pdv = 0.f;
-            if (qv && k < p.Tk) {
-              pr = exp2f(logit(p, __uint_as_float(rs[g8 * 8 + t]), bias_row, k, q) * kLog2e - lse2);
-              float dpv = __uint_as_float(rp[g8 * 8 + t]);
-              if (p.drop.p > 0.f) {
-                const bool kp = (keep >> t) & 1u;
-                dpv = kp ? dpv * p.drop.scale : 0.f;
-                pdv = kp ? pr * p.drop.scale : 0.f;
-              } else {
-                pdv = pr;
-              }
-              dsv = pr * (dpv - Dq);
-            }
-            pd[t] = pdv; ds[t] = dsv;
+            float x = fmaf(__uint_as_float(rs[g8 * 8 + t]), a2, bb[t]);
+            if (CAUSAL) x = (kbase + cc * 32 + g8 * 8 + t > qlim) ? x + cmask : x;
+            const float pr = ex2_approx(x - lse2);
+            const bool kp = (kb >> t) & 1u;
+            const float dpv = kp ? __uint_as_float(rp[g8 * 8 + t]) : 0.f;
+            pd[t] = kp ? pr : 0.f;
+            ds[t] = pr * fmaf(dpv, dscale, -Dq);
           }
           const uint32_t off = swz_off(row, c0 + g8 * 8);
           st_shared_v4(sP + off, pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]), pack_bf16(pd[6], pd[7]));
@@ -476,10 +538,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int t = 0; t < 32; t += 8) {
           uint4 a, c;
-          a.x = pack_bf16(__uint_as_float(rv[t]), __uint_as_float(rv[t + 1]));
-          a.y = pack_bf16(__uint_as_float(rv[t + 2]), __uint_as_float(rv[t + 3]));
-          a.z = pack_bf16(__uint_as_float(rv[t + 4]), __uint_as_float(rv[t + 5]));
-          a.w = pack_bf16(__uint_as_float(rv[t + 6]), __uint_as_float(rv[t + 7]));
+          a.x = pack_bf16(__uint_as_float(rv[t]) * dscale, __uint_as_float(rv[t + 1]) * dscale);
+          a.y = pack_bf16(__uint_as_float(rv[t + 2]) * dscale, __uint_as_float(rv[t + 3]) * dscale);
+          a.z = pack_bf16(__uint_as_float(rv[t + 4]) * dscale, __uint_as_float(rv[t + 5]) * dscale);
+          a.w = pack_bf16(__uint_as_float(rv[t + 6]) * dscale, __uint_as_float(rv[t + 7]) * dscale);
           c.x = pack_bf16(__uint_as_float(rk[t]) * p.alpha, __uint_as_float(rk[t + 1]) * p.alpha);
           c.y = pack_bf16(__uint_as_float(rk[t + 2]) * p.alpha, __uint_as_float(rk[t + 3]) * p.alpha);
           c.z = pack_bf16(__uint_as_float(rk[t + 4]) * p.alpha, __uint_as_float(rk[t + 5]) * p.alpha);
@@ -496,7 +558,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
 }
 
-constexpr size_t kBwdSmem = 1024 + (size_t)(2 + 2 + 2 + 2 + 2) * kTile16K + 8 * 12 + 64;
+constexpr size_t kBwdSmem = 1024 + (size_t)(2 + 2 + 2 + 2 + 2) * kTile16K + 128 + 512 + 64;
 
 // dst(bf16)[r, 0..cols) = src(fp32)[r, 0..cols)   (dq scratch -> the q columns of the fused dqkv buffer)
 __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
@@ -514,7 +576,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, 
   }
 }
 
-constexpr size_t kFwdSmem = 1024 + (size_t)(1 + 1 + 1 + 2) * kTile16K + 3072 + 8 * 10 + 64;
+constexpr size_t kFwdSmemFixed = 1024 + (size_t)(1 + 2 + 1 + 2) * kTile16K + 3072 + 8 * 14 + 64;   // + 512 B per kv block (bias table)
 
 }  // namespace
 
@@ -534,13 +596,17 @@ int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
   p.bias = bias; p.causal = causal; p.drop = drop;
   p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx); p.ctx_ld = ctx_ld; p.lse = lse;
   B200ST_CHECK((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && ctx_ld % 8 == 0, "ctx must be 16-byte aligned");
-  static bool attr = false;
-  if (!attr) {
-    B200ST_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
-    attr = true;
+  const size_t smem = kFwdSmemFixed + (size_t)((Tk + BKV - 1) / BKV) * 512;
+  B200ST_CHECK(smem <= 227 * 1024, "fused attention: Tk too large for the shared-memory bias table");
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[causal ? 1 : 0]) {
+    if (causal) B200ST_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else B200ST_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[causal ? 1 : 0] = smem;
   }
   dim3 grid((Tq + BQ - 1) / BQ, H, B);
-  launch_pdl(attn_fwd_kernel, grid, 320, kFwdSmem, s, tq, tk, tv, p);
+  if (causal) launch_pdl(attn_fwd_kernel<true>, grid, 320, smem, s, tq, tk, tv, p);
+  else launch_pdl(attn_fwd_kernel<false>, grid, 320, smem, s, tq, tk, tv, p);
   tc_count_launch();
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -572,13 +638,15 @@ int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
                  reinterpret_cast<uintptr_t>(dq_scratch)) & 15) == 0, "attention gradient buffers must be 16-byte aligned");
   static bool attr = false;
   if (!attr) {
-    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     attr = true;
   }
   const int64_t rows = (int64_t)B * Tq;
   B200ST_CUDA(cudaMemsetAsync(dq_scratch, 0, sizeof(float) * (size_t)rows * H * DH, s));
   dim3 grid((Tk + BKV - 1) / BKV, H, B);
-  launch_pdl(attn_bwd_kernel, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
+  if (causal) launch_pdl(attn_bwd_kernel<true>, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
+  else launch_pdl(attn_bwd_kernel<false>, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
   B200ST_LAUNCH_CHECK();
   const int64_t n8 = rows * (H * DH / 8);
   int64_t g = (n8 + 255) / 256;
