@@ -35,7 +35,8 @@ struct AttnParams {
   float* lse;                  // [B, H, Tq]  (natural log)
   // backward only
   const __nv_bfloat16* dctx; int64_t dctx_ld;
-  float* dq_acc; int64_t dq_ld;           // fp32 [B*Tq, H*64] (zero-initialised by the caller)
+  float* dq_acc; int64_t dq_ld;           // fp32 [B*Tq, H*64] (zeroed by attn_bwd_prep_kernel)
+  const float* dvec;                      // [B, H, Tq] rowsum(dO * O) (attn_bwd_prep_kernel)
   __nv_bfloat16* dk; int64_t dk_ld;       // [B*Tk, ...] view base already offset to the K columns; + h*64
   __nv_bfloat16* dv; int64_t dv_ld;
 };
@@ -80,6 +81,13 @@ __device__ __forceinline__ void load_keep64(const DropoutSpec& d, bool row_ok, i
                                             uint32_t (&keep)[2]) {
   keep[0] = keep[1] = 0xffffffffu;
   if (!(d.p > 0.f) || !row_ok) return;
+  if (d.bits && (Tkp & 63) == 0) {        // rows are 8-byte aligned in the bitmap: one 64-bit load
+    if (k0 < Tkp) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(d.bits + ((uint64_t)(row_bit0 + k0) >> 3)));
+      keep[0] = w.x; keep[1] = w.y;
+    }
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     if (k0 + 8 * g < Tkp) {
@@ -196,11 +204,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       softmax_bar();
     }
     float m = -INFINITY, l = 0.f;      // running row max (log2 domain, shared by both halves) and this half's partial sum
+    uint32_t keep[2], keep_next[2];
+    load_keep64(p.drop, q < p.Tq, row_g * p.Tkp, half * 64, p.Tkp, thresh, keep);
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
       const int kbase = j * BKV + half * 64;          // first key of this thread's 64 columns
-      uint32_t keep[2];
-      load_keep64(p.drop, q < p.Tq, row_g * p.Tkp, kbase, p.Tkp, thresh, keep);
       ptx::mbar_wait(s_full, ph);
       ptx::tc_fence_after();
       // logits (log2 domain) of this thread's 64 columns, kept in registers
@@ -211,6 +219,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(tS + lane_addr + half * 64, r0);
         ptx::tmem_ld_32x32b_x32(tS + lane_addr + half * 64 + 32, r1);
+        if (j + 1 < nblk) load_keep64(p.drop, q < p.Tq, row_g * p.Tkp, kbase + BKV, p.Tkp, thresh, keep_next);   // in flight during the math
+        __syncwarp();
         ptx::tmem_ld_wait();
       }
       float bmax = -INFINITY;
@@ -252,6 +262,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       l = l * corr + bsum;
       m = m_new;
+      keep[0] = keep_next[0]; keep[1] = keep_next[1];
       // rescale this half's 32 output columns (after the logits registers are dead) once the previous PV product has landed
       if (j > 0) {
         ptx::mbar_wait(o_ready, ph ^ 1u);
@@ -438,36 +449,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     const int kbase = jb * BKV + half * 64;
     const float4* bt4 = reinterpret_cast<const float4*>(btab + half * 64);
-    for (int i = 0; i < nq; ++i) {
+    // per-tile row scalars (D = rowsum(dO * O), LSE in the log2 domain: +inf on padding rows => P = 0, keep bits) are
+    // prefetched one tile ahead so their global-load latency hides behind the previous tile's math
+    auto load_row = [&](int i, float& Dq, float& lse2, uint32_t (&keep)[2]) {
       const int q = i * BQ + row;
       const bool qv = q < p.Tq;
       const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
-      const int qlim = q + (p.Tk - p.Tq);
-      uint32_t keep[2];
+      Dq = qv ? __ldg(p.dvec + row_g) : 0.f;
+      lse2 = qv ? __ldg(p.lse + row_g) * kLog2e : INFINITY;
       load_keep64(p.drop, qv, row_g * p.Tkp, kbase, p.Tkp, thresh, keep);
-      // D = rowsum(dO * O), LSE (log2 domain; +inf on padding rows => P = 0)
-      float Dq = 0.f, lse2 = INFINITY;
-      if (qv) {
-        const __nv_bfloat16* o_row = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH;
-        const __nv_bfloat16* do_row = p.dctx + ((int64_t)b * p.Tq + q) * p.dctx_ld + h * DH;
-        uint4 av[8], dv4[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          av[c] = __ldg(reinterpret_cast<const uint4*>(o_row + 8 * c));
-          dv4[c] = __ldg(reinterpret_cast<const uint4*>(do_row + 8 * c));
-        }
-        lse2 = p.lse[row_g] * kLog2e;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&av[c]);
-          const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dv4[c]);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 x = __bfloat1622float2(ah[t]), y = __bfloat1622float2(dh[t]);
-            Dq = fmaf(x.x, y.x, fmaf(x.y, y.y, Dq));
-          }
-        }
-      }
+    };
+    float Dq, lse2, Dq_n = 0.f, lse2_n = INFINITY;
+    uint32_t keep[2], keep_n[2] = {0xffffffffu, 0xffffffffu};
+    load_row(0, Dq, lse2, keep);
+    for (int i = 0; i < nq; ++i) {
+      const int q = i * BQ + row;
+      const bool qv = q < p.Tq;
+      const int qlim = q + (p.Tk - p.Tq);
+      if (i + 1 < nq) load_row(i + 1, Dq_n, lse2_n, keep_n);
+      __syncwarp();
       ptx::mbar_wait(sdp_full, (uint32_t)i & 1u);
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -523,6 +523,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(dq_empty);
+      Dq = Dq_n; lse2 = lse2_n; keep[0] = keep_n[0]; keep[1] = keep_n[1];
     }
     // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them); 32 columns per half ----
     const int kk = jb * BKV + row;
@@ -559,6 +560,39 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 constexpr size_t kBwdSmem = 1024 + (size_t)(2 + 2 + 2 + 2 + 2) * kTile16K + 128 + 512 + 64;
+
+// One warp per (b, q) row: zero the fp32 dQ accumulator row and compute D[b,h,q] = sum_c dO[b,q,h,c] * O[b,q,h,c].
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_t o_ld, const __nv_bfloat16* __restrict__ dout,
+                                     int64_t do_ld, float* __restrict__ dq_acc, float* __restrict__ dvec, int B, int H, int Tq) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * Tq;
+  const int chunks = H * (DH / 8);                  // 16-byte chunks per row; 8 chunks per head
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int b = (int)(r / Tq), q = (int)(r % Tq);
+    for (int c0 = 0; c0 < chunks; c0 += 32) {
+      const int c = c0 + lane;
+      float part = 0.f;
+      if (c < chunks) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + r * o_ld + 8 * c)), d = __ldg(reinterpret_cast<const uint4*>(dout + r * do_ld + 8 * c));
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = __bfloat1622float2(ah[t]), y = __bfloat1622float2(dh[t]);
+          part = fmaf(x.x, y.x, fmaf(x.y, y.y, part));
+        }
+        float4* z = reinterpret_cast<float4*>(dq_acc + r * (int64_t)H * DH + 8 * c);
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f); z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      if (c < chunks && (lane & 7) == 0) dvec[((int64_t)b * H + (c >> 3)) * Tq + q] = part;
+    }
+  }
+}
 
 // dst(bf16)[r, 0..cols) = src(fp32)[r, 0..cols)   (dq scratch -> the q columns of the fused dqkv buffer)
 __global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
@@ -643,7 +677,18 @@ int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
     attr = true;
   }
   const int64_t rows = (int64_t)B * Tq;
-  B200ST_CUDA(cudaMemsetAsync(dq_scratch, 0, sizeof(float) * (size_t)rows * H * DH, s));
+  float* dvec = dq_scratch + rows * H * DH;
+  p.dvec = dvec;
+  B200ST_CHECK((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dctx) & 15) == 0 && ctx_ld % 8 == 0 &&
+               dctx_ld % 8 == 0, "attention ctx / dctx must be 16-byte aligned");
+  {
+    int64_t gp = (rows + 7) / 8;
+    if (gp > 148 * 8) gp = 148 * 8;
+    launch_pdl(attn_bwd_prep_kernel, (int)gp, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(ctx), ctx_ld,
+               reinterpret_cast<const __nv_bfloat16*>(dctx), dctx_ld, dq_scratch, dvec, B, H, Tq);
+    g_kernel_launches += 1;
+    B200ST_LAUNCH_CHECK();
+  }
   dim3 grid((Tk + BKV - 1) / BKV, H, B);
   if (causal) launch_pdl(attn_bwd_kernel<true>, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
   else launch_pdl(attn_bwd_kernel<false>, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);

@@ -74,7 +74,7 @@ int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 
 // ---- fused attention (bf16, head dim 64): tcgen05 QK^T / PV with on-chip online softmax (attention.cu) ----
 // q/k/v/ctx/dctx/dq/dk/dv: bf16 views [B*T, ld], head h at columns [h*64, h*64+64); bias fp32 [B,Tk] or null;
-// lse fp32 [B,H,Tq] (written by forward, read by backward); dq_scratch fp32 [B*Tq, H*64].
+// lse fp32 [B,H,Tq] (written by forward, read by backward); dq_scratch fp32 [B*Tq, H*64] followed by [B*H*Tq] floats (rowsum(dO*O)).
 int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
                         int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
                         cudaStream_t s);

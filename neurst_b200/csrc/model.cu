@@ -532,7 +532,7 @@ static void alloc_scratch(Ctx& c, Scratch& sc, int B, int Tq_max, int Tk_max, in
     sc.dkv = c.act((int64_t)Mk_max * 2 * cf.d);
     sc.dF1 = c.act((int64_t)Mq_max * cf.ffn);
     sc.dh = c.f32((int64_t)Mq_max * cf.d);
-    sc.dq32 = c.f32((int64_t)Mq_max * cf.d);
+    sc.dq32 = c.f32((int64_t)Mq_max * (cf.d + cf.heads));   // + rowsum(dO * O) per (row, head)
   }
 }
 
