@@ -135,10 +135,70 @@ struct Arena {
   }
 };
 
+// Weight / bias gradients are off the backward critical path (nothing in the step reads them before the optimizer), so
+// they run on a second stream and fill the SMs the latency-bound dgrad chain leaves idle.  One process-wide stream +
+// three events; inside a CUDA-graph capture the event edges become graph dependencies (fork / join).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+static SideStream& side_stream() {
+  static SideStream ss;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (!getenv("B200ST_NO_SIDE_STREAM")) {
+      ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.done[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.done[1], cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  return ss;
+}
+
 struct Ctx {
   const Model& m;
   Buffers buf;
   cudaStream_t st;
+  // ---- side stream for weight gradients (backward of the full model only) ----
+  SideStream* side = nullptr;
+  bool side_pending[2] = {false, false};
+  int bwd_blocks = 0;
+  int cur_par = 0;
+  // Start of a backward block: picks the gradient-scratch parity and waits for the side-stream readers of that parity
+  // (issued two blocks ago) before the block overwrites it.
+  int begin_bwd_block() {
+    cur_par = (bwd_blocks++) & 1;
+    if (side && !dry && side_pending[cur_par]) {
+      if (cudaStreamWaitEvent(st, side->done[cur_par], 0) != cudaSuccess) launch_failed = true;
+      side_pending[cur_par] = false;
+    }
+    return cur_par;
+  }
+  // stream for a weight-gradient launch whose inputs were produced on `st` so far
+  cudaStream_t wgrad_stream() {
+    if (!side || dry) return st;
+    if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+      launch_failed = true;
+      return st;
+    }
+    return side->stream;
+  }
+  void wgrad_done(cudaStream_t s) {
+    if (!side || dry || s == st) return;
+    if (cudaEventRecord(side->done[cur_par], s) != cudaSuccess) launch_failed = true;
+    side_pending[cur_par] = true;
+  }
+  void join_side() {
+    if (!side || dry) return;
+    for (int i = 0; i < 2; ++i)
+      if (side_pending[i]) {
+        if (cudaStreamWaitEvent(st, side->done[i], 0) != cudaSuccess) launch_failed = true;
+        side_pending[i] = false;
+      }
+  }
   bool dry;        // planning pass: allocate only, launch nothing
   bool training;
   uint64_t seed;
@@ -243,8 +303,10 @@ static int linear_wgrad(Ctx& c, const void* X, int64_t ldx, const void* dY, int6
   g.C = c.G(w); g.c_dtype = F32; g.ldc = N;
   g.epi.accumulate = 1;
   g.splitk = 0;
-  RUN(gemm(g, c.st));
-  if (!b.empty()) RUN(colsum_accum(dY, c.adt, M, N, ldy, c.G(b), c.st));
+  cudaStream_t ws = c.wgrad_stream();
+  RUN(gemm(g, ws));
+  if (!b.empty()) RUN(colsum_accum(dY, c.adt, M, N, ldy, c.G(b), ws));
+  c.wgrad_done(ws);
   return 0;
 }
 
@@ -357,11 +419,14 @@ struct FfnSave {
 struct Scratch {   // shared transient buffers (sized for the largest sublayer)
   float* S = nullptr;       // [B,H,Tq,Tkp] fp32 logits / dP
   void* dS = nullptr;
-  void* dY = nullptr;       // [M,d]
+  // gradient operands of the weight-gradient GEMMs: double-buffered by backward-block parity (side-stream readers)
+  void* dY2[2] = {nullptr, nullptr};       // [M,d]
+  void* dqkv2[2] = {nullptr, nullptr};     // [M,3d]
+  void* dkv2[2] = {nullptr, nullptr};      // [Mk,2d]
+  void* dF12[2] = {nullptr, nullptr};      // [M,ffn]
+  void* dY = nullptr; void* dqkv = nullptr; void* dkv = nullptr; void* dF1 = nullptr;   // current block's buffers
+  void select(int par) { dY = dY2[par]; dqkv = dqkv2[par]; dkv = dkv2[par]; dF1 = dF12[par]; }
   void* dctx = nullptr;     // [M,d]
-  void* dqkv = nullptr;     // [M,3d]
-  void* dkv = nullptr;      // [Mk,2d]
-  void* dF1 = nullptr;      // [M,ffn]
   float* dh = nullptr;      // [M,d] fp32
   float* dq32 = nullptr;    // [M,d] fp32 (fused attention: dQ reduction across kv blocks)
 };
@@ -399,6 +464,7 @@ static int self_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_in
 }
 
 static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, float* dx_in, Scratch& sc, const AttnSave& sv) {
+  sc.select(c.begin_bwd_block());
   const Config& cf = c.m.cfg;
   const int d = cf.d, M = sv.dims.B * sv.dims.Tq;
   RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
@@ -452,6 +518,7 @@ static int cross_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_i
 
 static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, float* dx_in, float* dmem, Scratch& sc,
                                 const AttnSave& sv) {
+  sc.select(c.begin_bwd_block());
   const Config& cf = c.m.cfg;
   const int d = cf.d, M = sv.dims.B * sv.dims.Tq, Mk = sv.dims.B * sv.dims.Tk;
   RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
@@ -495,6 +562,7 @@ static int ffn_block_fwd(Ctx& c, const std::string& pre, const float* x_in, floa
 }
 
 static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, float* dx_in, Scratch& sc, const FfnSave& sv) {
+  sc.select(c.begin_bwd_block());
   const Config& cf = c.m.cfg;
   const int d = cf.d, f = cf.ffn, M = sv.M;
   RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
@@ -526,11 +594,14 @@ static void alloc_scratch(Ctx& c, Scratch& sc, int B, int Tq_max, int Tk_max, in
   sc.S = c.f32(pl);
   if (backward) {
     sc.dS = c.act(pl);
-    sc.dY = c.act((int64_t)Mq_max * cf.d);
+    for (int par = 0; par < 2; ++par) {
+      sc.dY2[par] = c.act((int64_t)Mq_max * cf.d);
+      sc.dqkv2[par] = c.act((int64_t)Mq_max * 3 * cf.d);
+      sc.dkv2[par] = c.act((int64_t)Mk_max * 2 * cf.d);
+      sc.dF12[par] = c.act((int64_t)Mq_max * cf.ffn);
+    }
+    sc.select(0);
     sc.dctx = c.act((int64_t)Mq_max * cf.d);
-    sc.dqkv = c.act((int64_t)Mq_max * 3 * cf.d);
-    sc.dkv = c.act((int64_t)Mk_max * 2 * cf.d);
-    sc.dF1 = c.act((int64_t)Mq_max * cf.ffn);
     sc.dh = c.f32((int64_t)Mq_max * cf.d);
     sc.dq32 = c.f32((int64_t)Mq_max * (cf.d + cf.heads));   // + rowsum(dO * O) per (row, head)
   }
@@ -778,6 +849,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   if (!backward) return 0;
 
   // =========================== backward ===========================
+  if (!c.dry && side_stream().ok) c.side = &side_stream();
   // logits layer: dE += dlogits^T dec_out ; db += colsum ; d_dec_out = dlogits E
   {
     GemmArgs g = gemm_defaults();
@@ -786,8 +858,11 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
     g.B = GemmOperand{ds.out, c.adt, 1, d, 0, 0};
     g.C = c.G("trg.emb"); g.c_dtype = F32; g.ldc = d;
     g.epi.accumulate = 1; g.splitk = 0;
-    RUN(gemm(g, c.st));
-    RUN(colsum_accum(dlogits, c.adt, Md, V, V, c.G("trg.bias"), c.st));
+    c.cur_par = 1;                       // dlogits is never reused: let the first backward block (parity 0) run ahead
+    cudaStream_t ws = c.wgrad_stream();
+    RUN(gemm(g, ws));
+    RUN(colsum_accum(dlogits, c.adt, Md, V, V, c.G("trg.bias"), ws));
+    c.wgrad_done(ws);
   }
   float* d_dec = c.f32((int64_t)Md * d);
   {
@@ -814,6 +889,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
     RUN(embed_bwd(b.src_ids, dx, c.G(tab), B, Ts, d, cf.share_src_trg_embedding ? V : cf.src_vocab,
                   c.drop(cf.postprocess_dropout, dropout_stream_id("enc.in_drop")), c.st));
   }
+  c.join_side();        // the optimizer / all-reduce on `st` must see every weight gradient
   return 0;
 }
 
