@@ -140,7 +140,7 @@ struct Arena {
 // three events; inside a CUDA-graph capture the event edges become graph dependencies (fork / join).
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, done[2] = {nullptr, nullptr}, bits_done = nullptr;
   bool ok = false;
 };
 static SideStream& side_stream() {
@@ -152,7 +152,8 @@ static SideStream& side_stream() {
       ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.done[0], cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&ss.done[1], cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&ss.done[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ss.bits_done, cudaEventDisableTiming) == cudaSuccess;
     }
   }
   return ss;
@@ -220,8 +221,16 @@ struct Ctx {
   // Dropout site `stream`.  The first (forward) use passes the element count: the keep-bits of the whole site are then
   // generated once into the workspace (one Philox call per 8 elements, full-occupancy kernel) and every consumer —
   // GEMM epilogues, fused attention, the backward pass — just reads bits.  Later uses return the memoised spec.
+  cudaEvent_t bits_event = nullptr;      // keep-bit generation running on the side stream: the first consumer waits
+  void wait_bits() {
+    if (bits_event) {
+      if (cudaStreamWaitEvent(st, bits_event, 0) != cudaSuccess) launch_failed = true;
+      bits_event = nullptr;
+    }
+  }
   DropoutSpec drop(float p, uint64_t stream, int64_t n_elems = 0) {
     if (!training || p <= 0.f) return no_dropout();
+    if (!dry) wait_bits();
     auto it = drop_memo.find(stream);
     if (it != drop_memo.end()) return it->second;
     DropoutSpec d{p, 1.f / (1.f - p), seed, stream, seed_dev, nullptr};
@@ -924,10 +933,21 @@ static int run_planned(const Model& m, const Buffers& buf, cudaStream_t st, F&& 
       g += ds.groups;
     }
     t.goff[t.n] = g;
-    B200ST_TRY(dropout_bits_multi(t, dry.seed, dry.seed_dev, reinterpret_cast<uint8_t*>(buf.workspace), st));
+    // The generator is pure ALU work: it runs on the side stream under the (bandwidth-bound) kernels that precede the
+    // first dropout consumer; Ctx::drop() makes `st` wait for it at that first consumer.
+    SideStream& ss = side_stream();
+    cudaStream_t bs = st;
+    if (ss.ok && cudaEventRecord(ss.fork, st) == cudaSuccess && cudaStreamWaitEvent(ss.stream, ss.fork, 0) == cudaSuccess) bs = ss.stream;
+    B200ST_TRY(dropout_bits_multi(t, dry.seed, dry.seed_dev, reinterpret_cast<uint8_t*>(buf.workspace), bs));
+    if (bs != st) {
+      B200ST_CUDA(cudaEventRecord(ss.bits_done, bs));
+      real.bits_event = ss.bits_done;
+    }
     real.bits_pregenerated = true;
   }
-  B200ST_TRY(body(real));
+  const int body_rc = body(real);
+  real.wait_bits();                     // no consumer ran (or an error unwound): still join the side stream
+  B200ST_TRY(body_rc);
   B200ST_CHECK(!real.launch_failed, "dropout bitmap kernel launch failed");
   if (real.bits_pregenerated) {
     B200ST_CHECK(real.drop_sites.size() == dry.drop_sites.size(),
