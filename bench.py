@@ -47,25 +47,43 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """One long-lived `nvidia-smi -lms 20` process; lines are stamped on arrival and only those that fall inside the
+    marked timed windows (resident + e2e regions, GPU under load) are summarised."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.samples = index, False, []
+        self.index, self.stop_flag, self.raw, self.windows, self.proc = index, False, [], [], None
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in r.stdout.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 6:
-                    self.samples.append(f)
+                    self.raw.append((time.time(), f))
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()            # the exact child we started
             except Exception:
                 pass
-            time.sleep(0.2)
+
+    @property
+    def samples(self):
+        inside = [f for (t, f) in self.raw if any(a <= t <= b for a, b in self.windows)]
+        return inside if inside else [f for (_, f) in self.raw[-3:]]
 
     def summary(self):
         if not self.samples:
@@ -209,19 +227,23 @@ def run_gpu(args):
         loss = trainer.train_step(db, seed=i + 1)
         losses.append(float(loss.item()))            # D2H read of the step's loss
 
-    for i in range(max(3, args.warmup)):
-        resident_step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                              # started before the warm-up so that it is streaming by the timed region
+    for i in range(max(3, args.warmup)):
+        resident_step(i)
     launches0 = lib.launch_count()
+    t_w0 = time.time()
     ms_total = timed(resident_step, args.steps)
+    sampler.mark(t_w0, time.time())
     launches = lib.launch_count() - launches0
-    sampler.stop_flag = True
     loss_val = float(losses[-1])
     for i in range(2):
         e2e_step(i)
+    t_w0 = time.time()
     ms_e2e = timed(e2e_step, args.steps)
+    sampler.mark(t_w0, time.time())
+    sampler.stop()
 
     # roofline pass (not timed): per-launch CUDA events around the tcgen05 GEMM launches of ONE step
     # (every rank runs the same steps — train_step contains the gradient all-reduce — only rank 0 reports)
@@ -272,17 +294,32 @@ def run_gpu(args):
         "e2e": {"value": frames / (ms_e2e / args.steps * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),
-        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": ach / peaks["tflops_sustained"], "traffic": None, "peak_source": peaks["source"],
-                     "algorithmic_flops_per_step": fl, "mflop_per_frame": fl / (B * T) / 1e6,
-                     "note": "whole training step (all kernels) against the sustained cuBLAS bf16 peak; "
-                             "tcgen05 GEMM launches alone: see gemm_kernels"},
     }
+    # roofline of the dominant kernel (tc_gemm_kernel: ~280 launches, ~55 % of the step): algorithmic FLOPs of those
+    # launches / their CUDA-event durations, measured on one eagerly launched step right after the timed region (a graph
+    # replay cannot be bracketed per kernel).  `traffic` = DRAM bytes per launch from the committed ncu pass
+    # (profiles/r01_gemm_traffic.json, same command), averaged like `achieved`.
+    step_rf = {"achieved": ach, "frac": ach / peaks["tflops_sustained"], "algorithmic_flops_per_step": fl,
+               "mflop_per_frame": fl / (B * T) / 1e6, "note": "all kernels of the step / step time"}
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_step"] / max(1, tj["launches"])
+    except Exception:
+        pass
     if gemm and gemm["ms"] > 0:
-        line["roofline"]["gemm_kernels"] = {"launches": gemm["launches"], "ms_per_step": gemm["ms"],
-                                            "tflops": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12,
-                                            "frac_of_peak": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / peaks["tflops_sustained"],
-                                            "share_of_step": gemm["ms"] / ms_step}
+        g_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05, all instantiations)", "achieved": g_tf,
+                            "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": g_tf / peaks["tflops_sustained"],
+                            "traffic": traffic, "peak_source": peaks["source"], "launches_per_step": gemm["launches"],
+                            "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
+                            "algorithmic_flops_per_launch": gemm["flops"] / max(1, gemm["launches"]),
+                            "share_of_step": gemm["ms"] / ms_step, "step": step_rf}
+    else:
+        line["roofline"] = {"bound": "tensor", "kernel": "whole step", "achieved": ach, "peak": peaks["tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                            "peak_source": peaks["source"], "step": step_rf}
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
