@@ -221,11 +221,17 @@ def run_gpu(args):
     def resident_step(i):
         losses.append(trainer.train_step(dev_batches[i % n_batches], seed=i + 1))
 
+    # e2e: the public host loop (neurst_b200.trainer.HostPipeline): every step copies its inputs from pinned host memory
+    # and reads its loss back; the copy of step i+1 and the read of step i-1 overlap the kernels of step i.
+    from neurst_b200.trainer import HostPipeline
+    import itertools
+    pipe = HostPipeline(trainer)
+    e2e_iter = pipe.run(itertools.cycle(host_batches), seed0=1000)
+
     def e2e_step(i):
-        hb = host_batches[i % n_batches]
-        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        loss = trainer.train_step(db, seed=i + 1)
-        losses.append(float(loss.item()))            # D2H read of the step's loss
+        v = next(e2e_iter)
+        if v is not None:
+            losses.append(v)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

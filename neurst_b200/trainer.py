@@ -102,6 +102,68 @@ class DataParallelTrainer:
         return out["loss"]
 
 
+class HostPipeline:
+    """Pipelined host loop around `DataParallelTrainer.train_step` — the role of `tf.data` prefetching plus Keras' async
+    metric reads in the reference's fit loop (neurst/exps/trainer.py:258-310, training/callbacks.py:209-238).
+
+    Every step still copies its own inputs host->device (from pinned memory) and reads its own loss device->host; the
+    copies of step i+1 run on a copy stream under the kernels of step i, and the loss of step i is read while step i+1
+    runs, so neither serialises with the GPU work."""
+
+    def __init__(self, trainer):
+        self.tr = trainer
+        self.dev = trainer.rt.device
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.staging = [None, None]                  # device copies of the host batches (double buffer)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of slot finished
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]  # compute stream no longer reads slot
+        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.h2d_bytes = 0
+
+    def _upload(self, slot, hb):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])
+            st = self.staging[slot]
+            if st is None or any(st[k].shape != v.shape for k, v in hb.items()):
+                st = self.staging[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in hb.items()}
+            for k, v in hb.items():
+                st[k].copy_(v, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in hb.values())
+
+    def run(self, host_batches, seed0=1):
+        """Generator over an iterable of pinned host batches: yields the float loss of every step, one step late (the
+        first `next()` yields None, `close()`/exhaustion is preceded by the last loss)."""
+        it = iter(host_batches)
+        cur = torch.cuda.current_stream(self.dev)
+        for s in range(2):
+            self.consumed[s].record(cur)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self._upload(0, nxt)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload(slot ^ 1, nxt)                       # H2D of step i+1 under the kernels of step i
+            cur.wait_event(self.ready[slot])
+            loss = self.tr.train_step(self.staging[slot], seed=seed0 + i)
+            self.consumed[slot].record(cur)
+            self.loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)   # D2H of this step's loss
+            self.loss_ready[slot].record(cur)
+            prev = None
+            if i > 0:
+                self.loss_ready[slot ^ 1].synchronize()
+                prev = float(self.loss_host[slot ^ 1])
+            yield prev
+            i += 1
+        self.loss_ready[(i - 1) & 1].synchronize()
+        yield float(self.loss_host[(i - 1) & 1])
+
+
 def build_speech_transformer_trainer(hparams_set="speech_transformer_s", vocab_size=8192, feature_dim=80, precision="bf16",
                                      label_smoothing=0.1, dropout=None, seed=1234, update_cycle=1, device=None, use_cuda_graph=False):
     hp = speech_transformer_hparams(hparams_set)

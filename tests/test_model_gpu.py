@@ -167,3 +167,24 @@ def test_fused_attention_matches_materialised_path():
         res.append((out["logits"].clone(), rt.grads.clone()))
     assert float((res[0][0] - res[1][0]).abs().max()) < 3e-2
     assert U.rel_err(res[0][1], res[1][1]) < 3e-2
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_host_pipeline_matches_plain_loop(graph):
+    """trainer.HostPipeline (H2D prefetch on a copy stream + one-step-late loss read) produces exactly the losses of the
+    plain `train_step` loop on the same batches / seeds (parameters updated by Adam in between)."""
+    from neurst_b200.trainer import build_speech_transformer_trainer, synthetic_batch, HostPipeline
+    def make():
+        tr, _ = build_speech_transformer_trainer("speech_transformer_s", vocab_size=96, precision="bf16", label_smoothing=0.1,
+                                                 seed=5, use_cuda_graph=graph)
+        return tr
+    hbs = [synthetic_batch(2, 120, 7, 96, seed=20 + i, pin=True) for i in range(3)]
+    a = make()
+    plain = [float(a.train_step({k: v.cuda() for k, v in hbs[i % 3].items()}, seed=100 + i)) for i in range(5)]
+    b = make()
+    pipe = HostPipeline(b)
+    got = [v for v in pipe.run([hbs[i % 3] for i in range(5)], seed0=100) if v is not None]
+    assert len(got) == 5
+    for x, y in zip(plain, got):
+        assert abs(x - y) < 2e-3 * max(1.0, abs(x)), (plain, got)
+    assert pipe.h2d_bytes == sum(v.numel() * v.element_size() for v in hbs[0].values())
