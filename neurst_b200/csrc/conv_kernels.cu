@@ -166,7 +166,8 @@ template <typename T, bool VEC, int CPL, bool CIN1>
 __global__ void __launch_bounds__(256, (CPL <= 8 ? 3 : 1)) conv1_fwd_kernel(const float* __restrict__ src, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, T* __restrict__ y, int B,
-                                                         int Tn, int F, int Cin, int C, int T1, int F1, int use_ln) {
+                                                         int Tn, int F, int Cin, int C, int T1, int F1, int use_ln,
+                                                         float* __restrict__ rstd_out) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float conv_smem[];
@@ -189,6 +190,17 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 3 : 1)) conv1_fwd_kernel(cons
     gather_taps(src, b, t1, f1, Tn, F, CIN1 ? 1 : Cin, xv);
     float z[CPL];
     taps.apply(xv, lane, Cin, C, z);
+    if (rstd_out) {
+      // normalised-save mode: store xhat and 1/sigma only; gamma, beta and the ReLU are applied by the consumers
+      // (im2col forward, conv1 backward), which removes the convolution recompute from the backward pass
+      float mean, rstd;
+      ln_stats<CPL, VEC>(z, lane, C, eps, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) z[i] = (z[i] - mean) * rstd;
+      if (lane == 0) rstd_out[pos] = rstd;
+      store_row<T, VEC, CPL>(y + pos * C, lane, C, z);
+      continue;
+    }
     if (use_ln) {
       float mean, rstd;
       ln_stats<CPL, VEC>(z, lane, C, eps, mean, rstd);
@@ -427,17 +439,115 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_fused_c256_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward from the saved normalised activations (C == 256, Cin == 1): col2im gather of dcol + ReLU' + LN' with xhat and
+// 1/sigma read back (no convolution recompute, no statistics), db/dgamma/dbeta partials, fbank im2col rows for dW1.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
+    const float* __restrict__ src, const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ xhat,
+    const float* __restrict__ rstd, const T* __restrict__ dcol, T* __restrict__ dz1, T* __restrict__ col1, int K1p,
+    float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn, int F, int T1, int F1, int T2,
+    int F2) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int C = 256;
+  __shared__ float sacc[3 * C];
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float greg[8], breg[8], a_db[8], a_dg[8], a_dbe[8];
+  ld8<float>(gamma + 8 * lane, greg);
+  ld8<float>(beta + 8 * lane, breg);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a_db[i] = a_dg[i] = a_dbe[i] = 0.f;
+  const int64_t npos = (int64_t)B * T1 * F1;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t per = (npos + nwarps - 1) / nwarps;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t pos = wid * per;
+  const int64_t pos_end = (pos + per < npos) ? pos + per : npos;
+  if (pos < pos_end) {
+    int f1 = (int)(pos % F1);
+    int t1 = (int)((pos / F1) % T1);
+    int b = (int)(pos / ((int64_t)F1 * T1));
+    const int tap_dt = lane / 3 - 1, tap_df = lane % 3 - 1;      // lanes 0..8 own one fbank tap each
+    for (; pos < pos_end; ++pos) {
+      float xv = 0.f;
+      if (lane < 9) {
+        const int t = 2 * t1 + tap_dt, f = 2 * f1 + tap_df;
+        if (t >= 0 && t < Tn && f >= 0 && f < F) xv = __ldg(&src[((int64_t)b * Tn + t) * F + f]);
+      }
+      float xh[8];
+      ld8<T>(xhat + pos * C + 8 * lane, xh);
+      const float rs = __ldg(rstd + pos);
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = 0.f;
+      const int kh0 = (t1 & 1) ? 0 : 1, nkh = (t1 & 1) ? 2 : 1;
+      const int kw0 = (f1 & 1) ? 0 : 1, nkw = (f1 & 1) ? 2 : 1;
+      for (int a = 0; a < nkh; ++a) {
+        const int kh = kh0 + 2 * a;
+        const int t2 = (t1 + 1 - kh) >> 1;
+        if (t2 >= T2) continue;
+        for (int c2 = 0; c2 < nkw; ++c2) {
+          const int kw = kw0 + 2 * c2;
+          const int f2 = (f1 + 1 - kw) >> 1;
+          if (f2 >= F2) continue;
+          const int64_t row = ((int64_t)b * T2 + t2) * F2 + f2;
+          float t8[8];
+          ld8<T>(dcol + (row * 9 + kh * 3 + kw) * C + 8 * lane, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] += t8[i];
+        }
+      }
+      float c1 = 0.f, c2s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!(fmaf(xh[i], greg[i], breg[i]) > 0.f)) d[i] = 0.f;      // ReLU' on y = xhat * gamma + beta
+        const float g = d[i] * greg[i];
+        c1 += g; c2s = fmaf(g, xh[i], c2s);
+        a_dg[i] = fmaf(d[i], xh[i], a_dg[i]); a_dbe[i] += d[i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { c1 += __shfl_xor_sync(0xffffffffu, c1, o); c2s += __shfl_xor_sync(0xffffffffu, c2s, o); }
+      c1 *= (1.0f / C); c2s *= (1.0f / C);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { d[i] = rs * (d[i] * greg[i] - c1 - xh[i] * c2s); a_db[i] += d[i]; }
+      st8<T>(dz1 + pos * C + 8 * lane, d);
+      if (lane < K1p) col1[pos * K1p + lane] = from_f32<T>(lane < 9 ? xv : 0.f);
+      if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = 8 * lane + i;
+    atomicAdd(&sacc[c], a_db[i]); atomicAdd(&sacc[C + c], a_dg[i]); atomicAdd(&sacc[2 * C + c], a_dbe[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&db[i], sacc[i]); atomicAdd(&dgamma[i], sacc[C + i]); atomicAdd(&dbeta[i], sacc[2 * C + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // im2col for the 3x3 stride-2 pad-1 conv2 (NHWC): one warp per (row, tap) chunk of C channels
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ y1, T* __restrict__ col, int B, int T1, int F1,
-                                                      int C, int T2, int F2) {
+                                                      int C, int T2, int F2, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta) {
   pdl_wait();
   pdl_trigger();
   const int64_t nchunks = (int64_t)B * T2 * F2 * 9;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   constexpr int EPV = 16 / sizeof(T);            // elements per 16-byte vector
+  // gamma != null: the source holds the normalised conv1 activations; y = relu(x * gamma + beta) is applied in flight
+  float g0[EPV], b0[EPV];
+  if (VEC && gamma) {
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) { const int c = lane * EPV + j; g0[j] = c < C ? gamma[c] : 0.f; b0[j] = c < C ? beta[c] : 0.f; }
+  }
   for (int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += warps_total) {
     const int tap = (int)(ch % 9);
     const int64_t row = ch / 9;
@@ -451,11 +561,25 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ y1, T
     if (VEC) {
       for (int c = lane * EPV; c < C; c += 32 * EPV) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (inside) v = __ldg(reinterpret_cast<const uint4*>(srcp + c));
+        if (inside) {
+          v = __ldg(reinterpret_cast<const uint4*>(srcp + c));
+          if (gamma) {
+            T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) {
+              const float gg = (c == lane * EPV) ? g0[j] : gamma[c + j], bb = (c == lane * EPV) ? b0[j] : beta[c + j];
+              e[j] = from_f32<T>(fmaxf(fmaf(to_f32(e[j]), gg, bb), 0.f));
+            }
+          }
+        }
         *reinterpret_cast<uint4*>(dst + c) = v;
       }
     } else {
-      for (int c = lane; c < C; c += 32) dst[c] = inside ? srcp[c] : from_f32<T>(0.f);
+      for (int c = lane; c < C; c += 32) {
+        float x = inside ? to_f32(srcp[c]) : 0.f;
+        if (inside && gamma) x = fmaxf(fmaf(x, gamma[c], beta[c]), 0.f);
+        dst[c] = from_f32<T>(x);
+      }
     }
   }
 }
@@ -467,8 +591,22 @@ static int pick_grid(int64_t npos, int per_block, int cap) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+static int conv1_fwd_launch(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
+                            void* y1, int y_dtype, int B, int T, int F, int Cin, int C, int use_ln, float* rstd_out, cudaStream_t s);
+
 int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
                       void* y1, int y_dtype, int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s) {
+  return conv1_fwd_launch(src, w, b, gamma, beta, eps, y1, y_dtype, B, T, F, Cin, C, use_ln, nullptr, s);
+}
+// normalised-save forward: xhat = LN-normalised conv1 output (no gamma/beta/ReLU) + 1/sigma per position
+int conv1_norm_fwd(const float* src, const float* w, const float* b, float eps, void* xhat, int dtype, float* rstd, int B, int T,
+                   int F, int Cin, int C, cudaStream_t s) {
+  B200ST_CHECK(rstd != nullptr, "conv1_norm_fwd needs the rstd buffer");
+  return conv1_fwd_launch(src, w, b, nullptr, nullptr, eps, xhat, dtype, B, T, F, Cin, C, 0, rstd, s);
+}
+
+static int conv1_fwd_launch(const float* src, const float* w, const float* b, const float* gamma, const float* beta, float eps,
+                            void* y1, int y_dtype, int B, int T, int F, int Cin, int C, int use_ln, float* rstd_out, cudaStream_t s) {
   B200ST_CHECK(C <= 512 && Cin >= 1 && Cin <= 4, "conv front-end supports C <= 512 and 1..4 input channels");
   const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
   const int64_t npos = (int64_t)B * T1 * F1;
@@ -479,7 +617,7 @@ int conv1_ln_relu_fwd(const float* src, const float* w, const float* b, const fl
   B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
 #define FWD(VEC, CPL, CIN1)                                                                                             \
   DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_kernel<TT, VEC, CPL, CIN1>, grid, 256, smem, s, src, w, b, gamma, beta, eps, (TT*)y1, \
-                                                                                        B, T, F, Cin, C, T1, F1, use_ln)))
+                                                                                        B, T, F, Cin, C, T1, F1, use_ln, rstd_out)))
   if (vec && C <= 256) { if (Cin == 1) FWD(true, 8, true); else FWD(true, 8, false); }
   else if (vec) { if (Cin == 1) FWD(true, 16, true); else FWD(true, 16, false); }
   else if (C <= 256) { if (Cin == 1) FWD(false, 8, true); else FWD(false, 8, false); }
@@ -526,15 +664,39 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
   return 0;
 }
 
+// backward of the normalised-save front-end (C == 256, Cin == 1, 16-byte aligned rows)
+int conv1_bwd_from_xhat(const float* src, const float* gamma, const float* beta, const void* xhat, const float* rstd,
+                        const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma, float* dbeta, int B,
+                        int T, int F, int C, cudaStream_t s) {
+  B200ST_CHECK(C == 256 && K1p >= 9 && K1p <= 32, "conv1_bwd_from_xhat supports C == 256, Cin == 1");
+  B200ST_CHECK(((reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(dcol) | reinterpret_cast<uintptr_t>(dz1) |
+                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "conv1 backward buffers must be 16-byte aligned");
+  const int T1 = (T + 1) / 2, F1 = (F + 1) / 2, T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
+  const int64_t npos = (int64_t)B * T1 * F1;
+  if (npos == 0) return 0;
+  const int grid = pick_grid(npos, 8 * 16, 148 * 3);
+  DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT>, grid, 256, 0, s, src, gamma, beta, (const TT*)xhat, rstd,
+                                        (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2)));
+  ++g_kernel_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
 int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, cudaStream_t s) {
+  return im2col_3x3s2_affine(y1, col, dtype, B, T1, F1, C, nullptr, nullptr, s);
+}
+
+// gamma/beta != null: col = im2col(relu(y1 * gamma + beta)) (y1 = normalised conv1 output)
+int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, const float* gamma, const float* beta,
+                        cudaStream_t s) {
   const int T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
   const int64_t nchunks = (int64_t)B * T2 * F2 * 9;
   if (nchunks == 0) return 0;
   const int grid = pick_grid(nchunks, 8, 148 * 16);
   const int esz = dtype == BF16 ? 2 : 4;
   const bool vec = ((C * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
-  if (vec) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2)));
-  else DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2)));
+  if (vec) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, gamma, beta)));
+  else DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, gamma, beta)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

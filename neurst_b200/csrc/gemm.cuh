@@ -85,6 +85,7 @@ TcDebug& tc_debug();
 int64_t tc_launch_count();
 void tc_count_launch();
 void tc_profile_begin();
+bool tc_profile_active();   // per-launch event timing on: the model keeps every launch on one stream
 int tc_profile_end(double* ms, double* flops, int64_t* launches);
 
 }  // namespace b200st

@@ -95,5 +95,14 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
                     float* dbeta, int B, int T, int F, int Cin, int C, int use_ln, cudaStream_t s);
 // col[(b,t2,f2), (kh,kw,c)] = y1[b, 2*t2+kh-1, 2*f2+kw-1, c] (zero outside)
 int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, cudaStream_t s);
+// normalised-save front-end (training path at C == 256, Cin == 1): conv1 stores xhat + 1/sigma, the im2col applies
+// gamma / beta / ReLU in flight, the backward reads xhat back instead of recomputing the convolution
+int conv1_norm_fwd(const float* src, const float* w, const float* b, float eps, void* xhat, int dtype, float* rstd, int B, int T,
+                   int F, int Cin, int C, cudaStream_t s);
+int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, const float* gamma, const float* beta,
+                        cudaStream_t s);
+int conv1_bwd_from_xhat(const float* src, const float* gamma, const float* beta, const void* xhat, const float* rstd,
+                        const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma, float* dbeta, int B,
+                        int T, int F, int C, cudaStream_t s);
 
 }  // namespace b200st

@@ -715,9 +715,13 @@ static int decoder_bwd(Ctx& c, const float* d_out, float* dx, float* dx_tmp, flo
 struct FrontSave {
   void* y1 = nullptr; void* col = nullptr; void* z2 = nullptr; void* y2 = nullptr;
   float* mean2 = nullptr; float* rstd2 = nullptr;
+  float* rstd1 = nullptr;    // normalised-save mode: y1 holds xhat of conv1's LayerNorm, rstd1 its 1/sigma
   int B = 0, T = 0, T1 = 0, F1 = 0, T2 = 0, F2 = 0;
   uint64_t s_in = 0;
 };
+
+// conv1's LayerNorm output is saved normalised (xhat + 1/sigma) instead of post-ReLU when the fast kernels apply
+static bool front_saves_xhat(const Config& cf) { return cf.conv_layer_norm && cf.channels == 256 && cf.in_channels == 1; }
 
 // src fp32 [B,T,F,Cin] -> x0 fp32 [B*T2, d] = dropout((dense(flatten(conv stack))) * sqrt(d) + pos)
 static int speech_front_fwd(Ctx& c, const float* src, int B, int T, float* x0, FrontSave& sv) {
@@ -733,9 +737,16 @@ static int speech_front_fwd(Ctx& c, const float* src, int B, int T, float* x0, F
   sv.y2 = c.act(R2 * C);
   sv.mean2 = c.f32(R2); sv.rstd2 = c.f32(R2);
   float* e0 = c.f32((int64_t)B * T2 * d);
-  RUN(conv1_ln_relu_fwd(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f,
-                        sv.y1, c.adt, B, T, F, cf.in_channels, C, cf.conv_layer_norm, c.st));
-  RUN(im2col_3x3s2(sv.y1, sv.col, c.adt, B, T1, F1, C, c.st));
+  if (front_saves_xhat(cf)) {
+    sv.rstd1 = c.f32(R1);
+    RUN(conv1_norm_fwd(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), 1e-6f, sv.y1, c.adt, sv.rstd1, B, T, F, cf.in_channels, C,
+                       c.st));
+    RUN(im2col_3x3s2_affine(sv.y1, sv.col, c.adt, B, T1, F1, C, c.P("src.ln1.gamma"), c.P("src.ln1.beta"), c.st));
+  } else {
+    RUN(conv1_ln_relu_fwd(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f,
+                          sv.y1, c.adt, B, T, F, cf.in_channels, C, cf.conv_layer_norm, c.st));
+    RUN(im2col_3x3s2(sv.y1, sv.col, c.adt, B, T1, F1, C, c.st));
+  }
   GemmEpilogue ez = gemm_defaults().epi;
   if (cf.conv_layer_norm) {
     B200ST_TRY(linear_fwd(c, sv.col, 9 * C, (int)R2, 9 * C, C, "src.conv2.kernel", "src.conv2.bias", ez, sv.z2, c.adt, C));
@@ -776,10 +787,15 @@ static int speech_front_bwd(Ctx& c, const float* src, const float* dx0, const Fr
   }
   B200ST_TRY(linear_wgrad(c, sv.col, 9 * C, dz2, C, (int)R2, 9 * C, C, "src.conv2.kernel", "src.conv2.bias"));
   B200ST_TRY(linear_dgrad(c, dz2, C, (int)R2, C, 9 * C, "src.conv2.kernel", e0, dcol, c.adt, 9 * C));
-  // fused: col2im gather + ReLU' + LN' (z1 recomputed) -> dz1, fbank im2col rows, db/dgamma/dbeta
-  RUN(conv1_bwd_fused(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f, sv.y1,
-                      dcol, c.adt, dz1, col1, K1p, c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F,
-                      cf.in_channels, C, cf.conv_layer_norm, c.st));
+  // fused: col2im gather + ReLU' + LN' -> dz1, fbank im2col rows, db/dgamma/dbeta (xhat read back, or z1 recomputed)
+  if (front_saves_xhat(cf)) {
+    RUN(conv1_bwd_from_xhat(src, c.P("src.ln1.gamma"), c.P("src.ln1.beta"), sv.y1, sv.rstd1, dcol, c.adt, dz1, col1, K1p,
+                            c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F, C, c.st));
+  } else {
+    RUN(conv1_bwd_fused(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f, sv.y1,
+                        dcol, c.adt, dz1, col1, K1p, c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F,
+                        cf.in_channels, C, cf.conv_layer_norm, c.st));
+  }
   {
     // dW1[9*Cin, C] += col1^T dz1   (split-K tcgen05 GEMM over all B*T1*F1 positions)
     GemmArgs g = gemm_defaults();
@@ -858,7 +874,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   if (!backward) return 0;
 
   // =========================== backward ===========================
-  if (!c.dry && side_stream().ok) c.side = &side_stream();
+  if (!c.dry && side_stream().ok && !tc_profile_active()) c.side = &side_stream();
   // logits layer: dE += dlogits^T dec_out ; db += colsum ; d_dec_out = dlogits E
   {
     GemmArgs g = gemm_defaults();

@@ -702,6 +702,7 @@ void tc_profile_begin() {
   g_prof_recs.clear();
   g_prof = true;
 }
+bool tc_profile_active() { return g_prof; }
 int tc_profile_end(double* ms, double* flops, int64_t* launches) {
   g_prof = false;
   double tms = 0, tf = 0;

@@ -78,7 +78,7 @@ def _worker(rank, world, port, q):
     tr.broadcast_parameters()
     for micro in range(4):                              # 2 optimizer steps of 2 micro-batches each
         tr.train_step(_batch(cfg, 100 * rank + micro))
-    q.put((rank, model.runtime.params.clone(), tr.global_step))
+    q.put((rank, model.runtime.params.detach().cpu().numpy().copy(), tr.global_step))   # by value: no fd passing after exit
     dist.barrier()
     dist.destroy_process_group()
 
@@ -91,6 +91,7 @@ def test_two_rank_data_parallel_matches_manual_average():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
+    res = [(r, torch.from_numpy(a), n) for r, a, n in res]
     for p in procs:
         p.join(60)
     assert res[0][2] == 2 and res[1][2] == 2

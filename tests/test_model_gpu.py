@@ -38,8 +38,9 @@ def test_forward_bf16_vs_reference_fixture():
 
 @pytest.mark.parametrize("precision,tol_logits,tol_grad", [("fp32", 1e-4, 2e-4), ("bf16", 6e-2, 1e-1)])
 @pytest.mark.parametrize("dropout", [0.0, 0.1])
-def test_forward_backward_vs_oracle(precision, tol_logits, tol_grad, dropout):
-    cfg = dict(model="speech", d=64, heads=4, enc_layers=2, dec_layers=2, ffn=128, channels=64, feat=80, in_channels=1, vocab=96)
+@pytest.mark.parametrize("channels", [64, 256])      # 256 = the production front-end kernels (normalised-save conv1 path)
+def test_forward_backward_vs_oracle(precision, tol_logits, tol_grad, dropout, channels):
+    cfg = dict(model="speech", d=64, heads=4, enc_layers=2, dec_layers=2, ffn=128, channels=channels, feat=80, in_channels=1, vocab=96)
     P = R.init_params(cfg, seed=7, random_bias=True)
     B, T, Lq = 3, 61, 9
     batch = U.synthetic_speech_batch(cfg, B, T, Lq, seed=3)
