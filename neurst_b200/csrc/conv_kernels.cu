@@ -214,6 +214,79 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 3 : 1)) conv1_fwd_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// conv1 forward, production shape (C == 256, Cin == 1): the lane's 9 x 8 filter taps live in registers (no shared-memory
+// traffic: the generic kernel is LDS-bound), the 9 fbank taps of a position are fetched by lanes 0..8 one position
+// ahead and broadcast with shuffles, each warp walks a contiguous range of positions.
+// SAVE: store xhat + 1/sigma (normalised-save mode); else y = relu(LN(z) * gamma + beta).
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool SAVE>
+__global__ void __launch_bounds__(256, 2) conv1_fwd_c256_kernel(const float* __restrict__ src, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, T* __restrict__ y,
+                                                                float* __restrict__ rstd_out, int B, int Tn, int F, int T1, int F1) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int C = 256;
+  const int lane = threadIdx.x & 31;
+  float wreg[9][8], breg[8], greg[8], bereg[8];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) ld8<float>(w + tp * C + 8 * lane, wreg[tp]);
+  ld8<float>(bias + 8 * lane, breg);
+  if (!SAVE) { ld8<float>(gamma + 8 * lane, greg); ld8<float>(beta + 8 * lane, bereg); }
+  const int64_t npos = (int64_t)B * T1 * F1;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t per = (npos + nwarps - 1) / nwarps;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t pos = wid * per;
+  const int64_t pos_end = (pos + per < npos) ? pos + per : npos;
+  if (pos >= pos_end) return;
+  int f1 = (int)(pos % F1);
+  int t1 = (int)((pos / F1) % T1);
+  int b = (int)(pos / ((int64_t)F1 * T1));
+  const int tap_dt = lane / 3 - 1, tap_df = lane % 3 - 1;      // lanes 0..8 own one fbank tap each
+  auto load_tap = [&](int bb, int tt1, int ff1) {
+    float v = 0.f;
+    if (lane < 9) {
+      const int t = 2 * tt1 + tap_dt, f = 2 * ff1 + tap_df;
+      if (t >= 0 && t < Tn && f >= 0 && f < F) v = __ldg(&src[((int64_t)bb * Tn + t) * F + f]);
+    }
+    return v;
+  };
+  float xv_next = load_tap(b, t1, f1);
+  for (; pos < pos_end; ++pos) {
+    const float xv = xv_next;
+    if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
+    if (pos + 1 < pos_end) xv_next = load_tap(b, t1, f1);        // next position's taps: in flight during the math
+    float z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = breg[i];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const float x = __shfl_sync(0xffffffffu, xv, tp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = fmaf(x, wreg[tp][i], z[i]);
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1 += z[i];
+    const float mean = warp_sum(s1) * (1.0f / C);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { z[i] -= mean; s2 = fmaf(z[i], z[i], s2); }
+    const float rstd = 1.0f / sqrtf(warp_sum(s2) * (1.0f / C) + eps);
+    if (SAVE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] *= rstd;
+      if (lane == 0) rstd_out[pos] = rstd;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = fmaxf(fmaf(z[i] * rstd, greg[i], bereg[i]), 0.f);
+    }
+    st8<T>(y + pos * C + 8 * lane, z);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused conv2-dgrad gather (col2im) + ReLU' + LN' of conv1 (recompute) -> dz1, im2col of src, db/dgamma/dbeta
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool VEC, int CPL, bool CIN1>
@@ -444,7 +517,7 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_fused_c256_kernel(
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
-    const float* __restrict__ src, const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ xhat,
+    const float* __restrict__ src, const T* __restrict__ gamma, const T* __restrict__ beta, const T* __restrict__ xhat,
     const float* __restrict__ rstd, const T* __restrict__ dcol, T* __restrict__ dz1, T* __restrict__ col1, int K1p,
     float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn, int F, int T1, int F1, int T2,
     int F2) {
@@ -456,8 +529,8 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
   __syncthreads();
   const int lane = threadIdx.x & 31;
   float greg[8], breg[8], a_db[8], a_dg[8], a_dbe[8];
-  ld8<float>(gamma + 8 * lane, greg);
-  ld8<float>(beta + 8 * lane, breg);
+  ld8<T>(gamma + 8 * lane, greg);       // affine parameters exactly as the forward used them (bf16 shadow in bf16 mode)
+  ld8<T>(beta + 8 * lane, breg);
 #pragma unroll
   for (int i = 0; i < 8; ++i) a_db[i] = a_dg[i] = a_dbe[i] = 0.f;
   const int64_t npos = (int64_t)B * T1 * F1;
@@ -532,22 +605,52 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
 // ---------------------------------------------------------------------------------------------
 // im2col for the 3x3 stride-2 pad-1 conv2 (NHWC): one warp per (row, tap) chunk of C channels
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+// y = relu(x * gamma + beta) on one 16-byte vector (affine parameters in the activation dtype: for bf16 they come from
+// the bf16 shadow arena and the math is packed HFMA2.BF16 / HMNMX2 — the same rounding the backward's ReLU mask assumes)
+__device__ __forceinline__ uint4 affine_relu_vec(uint4 v, const __nv_bfloat162 (&g)[4], const __nv_bfloat162 (&b)[4]) {
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __hmax2(__hfma2(h[j], g[j], b[j]), zero);
+  return v;
+}
+__device__ __forceinline__ uint4 affine_relu_vec(uint4 v, const float (&g)[4], const float (&b)[4]) {
+  float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) f[j] = fmaxf(fmaf(f[j], g[j], b[j]), 0.f);
+  return v;
+}
+template <typename T> struct AffineRegs;
+template <> struct AffineRegs<__nv_bfloat16> {
+  __nv_bfloat162 g[4], b[4];
+  __device__ __forceinline__ void load(const __nv_bfloat16* gamma, const __nv_bfloat16* beta, int c) {
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c)), bv = __ldg(reinterpret_cast<const uint4*>(beta + c));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { g[j] = reinterpret_cast<const __nv_bfloat162*>(&gv)[j]; b[j] = reinterpret_cast<const __nv_bfloat162*>(&bv)[j]; }
+  }
+};
+template <> struct AffineRegs<float> {
+  float g[4], b[4];
+  __device__ __forceinline__ void load(const float* gamma, const float* beta, int c) {
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + c)), bv = __ldg(reinterpret_cast<const float4*>(beta + c));
+    g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w; b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+  }
+};
+
+// gamma != null: the source holds the normalised conv1 activations; y = relu(x * gamma + beta) is applied in flight.
+// ONE: C == 32 vectors, i.e. each lane owns exactly one 16-byte vector of the row (affine parameters stay in registers).
+template <typename T, bool VEC, bool ONE>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ y1, T* __restrict__ col, int B, int T1, int F1,
-                                                      int C, int T2, int F2, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta) {
+                                                      int C, int T2, int F2, const T* __restrict__ gamma,
+                                                      const T* __restrict__ beta) {
   pdl_wait();
   pdl_trigger();
   const int64_t nchunks = (int64_t)B * T2 * F2 * 9;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   constexpr int EPV = 16 / sizeof(T);            // elements per 16-byte vector
-  // gamma != null: the source holds the normalised conv1 activations; y = relu(x * gamma + beta) is applied in flight
-  float g0[EPV], b0[EPV];
-  if (VEC && gamma) {
-#pragma unroll
-    for (int j = 0; j < EPV; ++j) { const int c = lane * EPV + j; g0[j] = c < C ? gamma[c] : 0.f; b0[j] = c < C ? beta[c] : 0.f; }
-  }
+  AffineRegs<T> ar;
+  if (VEC && ONE && gamma) ar.load(gamma, beta, lane * EPV);
   for (int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += warps_total) {
     const int tap = (int)(ch % 9);
     const int64_t row = ch / 9;
@@ -558,26 +661,26 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ y1, T
     const bool inside = t >= 0 && t < T1 && f >= 0 && f < F1;
     T* dst = col + (row * 9 + tap) * C;
     const T* srcp = y1 + (((int64_t)b * T1 + (inside ? t : 0)) * F1 + (inside ? f : 0)) * C;
-    if (VEC) {
+    if (VEC && ONE) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (inside) {
+        v = __ldg(reinterpret_cast<const uint4*>(srcp + lane * EPV));
+        if (gamma) v = affine_relu_vec(v, ar.g, ar.b);
+      }
+      *reinterpret_cast<uint4*>(dst + lane * EPV) = v;
+    } else if (VEC) {
       for (int c = lane * EPV; c < C; c += 32 * EPV) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (inside) {
           v = __ldg(reinterpret_cast<const uint4*>(srcp + c));
-          if (gamma) {
-            T* e = reinterpret_cast<T*>(&v);
-#pragma unroll
-            for (int j = 0; j < EPV; ++j) {
-              const float gg = (c == lane * EPV) ? g0[j] : gamma[c + j], bb = (c == lane * EPV) ? b0[j] : beta[c + j];
-              e[j] = from_f32<T>(fmaxf(fmaf(to_f32(e[j]), gg, bb), 0.f));
-            }
-          }
+          if (gamma) { AffineRegs<T> a2; a2.load(gamma, beta, c); v = affine_relu_vec(v, a2.g, a2.b); }
         }
         *reinterpret_cast<uint4*>(dst + c) = v;
       }
     } else {
       for (int c = lane; c < C; c += 32) {
         float x = inside ? to_f32(srcp[c]) : 0.f;
-        if (inside && gamma) x = fmaxf(fmaf(x, gamma[c], beta[c]), 0.f);
+        if (inside && gamma) x = fmaxf(fmaf(x, to_f32(gamma[c]), to_f32(beta[c])), 0.f);
         dst[c] = from_f32<T>(x);
       }
     }
@@ -613,6 +716,15 @@ static int conv1_fwd_launch(const float* src, const float* w, const float* b, co
   if (npos == 0) return 0;
   const int grid = pick_grid(npos, 8 * 4, 148 * 12);
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0);
+  if (vec && C == 256 && Cin == 1 && (use_ln || rstd_out) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
+      ((reinterpret_cast<uintptr_t>(b) & 15) == 0) && (rstd_out || (((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0))) {
+    const int grid1 = pick_grid(npos, 8 * 16, 148 * 2);
+    if (rstd_out) DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_c256_kernel<TT, true>, grid1, 256, 0, s, src, w, b, gamma, beta, eps, (TT*)y1, rstd_out, B, T, F, T1, F1)));
+    else DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_c256_kernel<TT, false>, grid1, 256, 0, s, src, w, b, gamma, beta, eps, (TT*)y1, rstd_out, B, T, F, T1, F1)));
+    ++g_kernel_launches;
+    B200ST_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)(9 * Cin + 1) * ((C + 255) & ~255) * sizeof(float);
   B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
 #define FWD(VEC, CPL, CIN1)                                                                                             \
@@ -665,7 +777,7 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
 }
 
 // backward of the normalised-save front-end (C == 256, Cin == 1, 16-byte aligned rows)
-int conv1_bwd_from_xhat(const float* src, const float* gamma, const float* beta, const void* xhat, const float* rstd,
+int conv1_bwd_from_xhat(const float* src, const void* gamma, const void* beta, const void* xhat, const float* rstd,
                         const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma, float* dbeta, int B,
                         int T, int F, int C, cudaStream_t s) {
   B200ST_CHECK(C == 256 && K1p >= 9 && K1p <= 32, "conv1_bwd_from_xhat supports C == 256, Cin == 1");
@@ -675,7 +787,7 @@ int conv1_bwd_from_xhat(const float* src, const float* gamma, const float* beta,
   const int64_t npos = (int64_t)B * T1 * F1;
   if (npos == 0) return 0;
   const int grid = pick_grid(npos, 8 * 16, 148 * 3);
-  DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT>, grid, 256, 0, s, src, gamma, beta, (const TT*)xhat, rstd,
+  DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT>, grid, 256, 0, s, src, (const TT*)gamma, (const TT*)beta, (const TT*)xhat, rstd,
                                         (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
@@ -686,17 +798,20 @@ int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, in
   return im2col_3x3s2_affine(y1, col, dtype, B, T1, F1, C, nullptr, nullptr, s);
 }
 
-// gamma/beta != null: col = im2col(relu(y1 * gamma + beta)) (y1 = normalised conv1 output)
-int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, const float* gamma, const float* beta,
+// gamma/beta != null (in the activation dtype): col = im2col(relu(y1 * gamma + beta)) (y1 = normalised conv1 output)
+int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, const void* gamma, const void* beta,
                         cudaStream_t s) {
   const int T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
   const int64_t nchunks = (int64_t)B * T2 * F2 * 9;
   if (nchunks == 0) return 0;
-  const int grid = pick_grid(nchunks, 8, 148 * 16);
+  const int grid = pick_grid(nchunks, 8 * 8, 148 * 16);
   const int esz = dtype == BF16 ? 2 : 4;
-  const bool vec = ((C * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0);
-  if (vec) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, gamma, beta)));
-  else DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, gamma, beta)));
+  const bool vec = ((C * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
+  const bool one = vec && C * esz == 32 * 16;
+  if (one) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true, true>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, (const TT*)gamma, (const TT*)beta)));
+  else if (vec) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, (const TT*)gamma, (const TT*)beta)));
+  else DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, false, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, (const TT*)gamma, (const TT*)beta)));
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

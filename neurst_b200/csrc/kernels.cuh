@@ -99,9 +99,9 @@ int im2col_3x3s2(const void* y1, void* col, int dtype, int B, int T1, int F1, in
 // gamma / beta / ReLU in flight, the backward reads xhat back instead of recomputing the convolution
 int conv1_norm_fwd(const float* src, const float* w, const float* b, float eps, void* xhat, int dtype, float* rstd, int B, int T,
                    int F, int Cin, int C, cudaStream_t s);
-int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, const float* gamma, const float* beta,
-                        cudaStream_t s);
-int conv1_bwd_from_xhat(const float* src, const float* gamma, const float* beta, const void* xhat, const float* rstd,
+int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int F1, int C, const void* gamma, const void* beta,
+                        cudaStream_t s);   // gamma / beta in the activation dtype (bf16 shadow or fp32 master)
+int conv1_bwd_from_xhat(const float* src, const void* gamma, const void* beta, const void* xhat, const float* rstd,
                         const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma, float* dbeta, int B,
                         int T, int F, int C, cudaStream_t s);
 

@@ -741,7 +741,7 @@ static int speech_front_fwd(Ctx& c, const float* src, int B, int T, float* x0, F
     sv.rstd1 = c.f32(R1);
     RUN(conv1_norm_fwd(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), 1e-6f, sv.y1, c.adt, sv.rstd1, B, T, F, cf.in_channels, C,
                        c.st));
-    RUN(im2col_3x3s2_affine(sv.y1, sv.col, c.adt, B, T1, F1, C, c.P("src.ln1.gamma"), c.P("src.ln1.beta"), c.st));
+    RUN(im2col_3x3s2_affine(sv.y1, sv.col, c.adt, B, T1, F1, C, c.W("src.ln1.gamma", 0, C).ptr, c.W("src.ln1.beta", 0, C).ptr, c.st));
   } else {
     RUN(conv1_ln_relu_fwd(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f,
                           sv.y1, c.adt, B, T, F, cf.in_channels, C, cf.conv_layer_norm, c.st));
@@ -789,7 +789,7 @@ static int speech_front_bwd(Ctx& c, const float* src, const float* dx0, const Fr
   B200ST_TRY(linear_dgrad(c, dz2, C, (int)R2, C, 9 * C, "src.conv2.kernel", e0, dcol, c.adt, 9 * C));
   // fused: col2im gather + ReLU' + LN' -> dz1, fbank im2col rows, db/dgamma/dbeta (xhat read back, or z1 recomputed)
   if (front_saves_xhat(cf)) {
-    RUN(conv1_bwd_from_xhat(src, c.P("src.ln1.gamma"), c.P("src.ln1.beta"), sv.y1, sv.rstd1, dcol, c.adt, dz1, col1, K1p,
+    RUN(conv1_bwd_from_xhat(src, c.W("src.ln1.gamma", 0, C).ptr, c.W("src.ln1.beta", 0, C).ptr, sv.y1, sv.rstd1, dcol, c.adt, dz1, col1, K1p,
                             c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F, C, c.st));
   } else {
     RUN(conv1_bwd_fused(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f, sv.y1,
