@@ -46,6 +46,27 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* ds
   *reinterpret_cast<uint4*>(dst) = pk;
 }
 
+// 8 consecutive elements held in raw form (prefetch registers: 16 B for bf16, 32 B for fp32)
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1); }
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 // Channel owned by (lane, i): VEC => 8 contiguous channels per lane per 256-channel group; else lane-strided.
 template <bool VEC> __device__ __forceinline__ int chan(int lane, int i) {
   return VEC ? (8 * lane + 256 * (i >> 3) + (i & 7)) : (lane + 32 * i);
@@ -516,7 +537,7 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_fused_c256_kernel(
 // 1/sigma read back (no convolution recompute, no statistics), db/dgamma/dbeta partials, fbank im2col rows for dW1.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
+__global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
     const float* __restrict__ src, const T* __restrict__ gamma, const T* __restrict__ beta, const T* __restrict__ xhat,
     const float* __restrict__ rstd, const T* __restrict__ dcol, T* __restrict__ dz1, T* __restrict__ col1, int K1p,
     float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn, int F, int T1, int F1, int T2,
@@ -544,35 +565,45 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
     int t1 = (int)((pos / F1) % T1);
     int b = (int)(pos / ((int64_t)F1 * T1));
     const int tap_dt = lane / 3 - 1, tap_df = lane % 3 - 1;      // lanes 0..8 own one fbank tap each
-    for (; pos < pos_end; ++pos) {
-      float xv = 0.f;
+    // every global load of a position (fbank tap, xhat row, 1/sigma, <= 4 dcol rows) is issued one position ahead
+    struct Loads { Vec8<T> xh, dc[4]; float rs, xv; };
+    auto issue = [&](int64_t p, int bb, int tt1, int ff1, Loads& L) {
+      L.xv = 0.f;
       if (lane < 9) {
-        const int t = 2 * t1 + tap_dt, f = 2 * f1 + tap_df;
-        if (t >= 0 && t < Tn && f >= 0 && f < F) xv = __ldg(&src[((int64_t)b * Tn + t) * F + f]);
+        const int t = 2 * tt1 + tap_dt, f = 2 * ff1 + tap_df;
+        if (t >= 0 && t < Tn && f >= 0 && f < F) L.xv = __ldg(&src[((int64_t)bb * Tn + t) * F + f]);
       }
-      float xh[8];
-      ld8<T>(xhat + pos * C + 8 * lane, xh);
-      const float rs = __ldg(rstd + pos);
-      float d[8];
+      L.xh.load(xhat + p * C + 8 * lane);
+      L.rs = __ldg(rstd + p);
+      // col2im: t1 even -> kh = 1 ; t1 odd -> kh in {0, 2} (same along f); slot = 2 * a + c2
+      const int kh0 = (tt1 & 1) ? 0 : 1, kw0 = (ff1 & 1) ? 0 : 1;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = 0.f;
-      const int kh0 = (t1 & 1) ? 0 : 1, nkh = (t1 & 1) ? 2 : 1;
-      const int kw0 = (f1 & 1) ? 0 : 1, nkw = (f1 & 1) ? 2 : 1;
-      for (int a = 0; a < nkh; ++a) {
-        const int kh = kh0 + 2 * a;
-        const int t2 = (t1 + 1 - kh) >> 1;
-        if (t2 >= T2) continue;
-        for (int c2 = 0; c2 < nkw; ++c2) {
-          const int kw = kw0 + 2 * c2;
-          const int f2 = (f1 + 1 - kw) >> 1;
-          if (f2 >= F2) continue;
-          const int64_t row = ((int64_t)b * T2 + t2) * F2 + f2;
-          float t8[8];
-          ld8<T>(dcol + (row * 9 + kh * 3 + kw) * C + 8 * lane, t8);
+      for (int a = 0; a < 2; ++a) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] += t8[i];
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int kh = kh0 + 2 * a, kw = kw0 + 2 * c2;
+          const int t2 = (tt1 + 1 - kh) >> 1, f2 = (ff1 + 1 - kw) >> 1;
+          const bool ok = (a == 0 || (tt1 & 1)) && (c2 == 0 || (ff1 & 1)) && t2 < T2 && f2 < F2;
+          if (ok) L.dc[2 * a + c2].load(dcol + ((((int64_t)bb * T2 + t2) * F2 + f2) * 9 + kh * 3 + kw) * C + 8 * lane);
+          else L.dc[2 * a + c2].zero();
         }
       }
+    };
+    Loads cur, nxt;
+    issue(pos, b, t1, f1, cur);
+    for (; pos < pos_end; ++pos) {
+      if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
+      if (pos + 1 < pos_end) issue(pos + 1, b, t1, f1, nxt);
+      float xh[8], d[8], t8[8];
+      cur.xh.get(xh);
+      cur.dc[0].get(d);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        cur.dc[k].get(t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += t8[i];
+      }
+      const float rs = cur.rs;
       float c1 = 0.f, c2s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -587,8 +618,8 @@ __global__ void __launch_bounds__(256, 3) conv1_bwd_xhat_c256_kernel(
 #pragma unroll
       for (int i = 0; i < 8; ++i) { d[i] = rs * (d[i] * greg[i] - c1 - xh[i] * c2s); a_db[i] += d[i]; }
       st8<T>(dz1 + pos * C + 8 * lane, d);
-      if (lane < K1p) col1[pos * K1p + lane] = from_f32<T>(lane < 9 ? xv : 0.f);
-      if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
+      if (lane < K1p) col1[pos * K1p + lane] = from_f32<T>(lane < 9 ? cur.xv : 0.f);
+      cur = nxt;
     }
   }
 #pragma unroll
@@ -786,7 +817,7 @@ int conv1_bwd_from_xhat(const float* src, const void* gamma, const void* beta, c
   const int T1 = (T + 1) / 2, F1 = (F + 1) / 2, T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
   const int64_t npos = (int64_t)B * T1 * F1;
   if (npos == 0) return 0;
-  const int grid = pick_grid(npos, 8 * 16, 148 * 3);
+  const int grid = pick_grid(npos, 8 * 16, 148 * 2);
   DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT>, grid, 256, 0, s, src, (const TT*)gamma, (const TT*)beta, (const TT*)xhat, rstd,
                                         (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2)));
   ++g_kernel_launches;

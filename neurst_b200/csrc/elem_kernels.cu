@@ -229,10 +229,8 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__
                                                           int cols, int relu) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sm[];   // [2][cols] block partials
+  extern __shared__ float sm[];   // [nwarps][2][cols] per-warp partials (no shared-memory atomics)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
   float gam[NV][4], bet[NV][4], dg_acc[NV][4], db_acc[NV][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -278,18 +276,25 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__
       }
     }
   }
+  float* mine = sm + (size_t)warp * 2 * cols;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = 4 * lane + 128 * i;
     if (c < cols) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { atomicAdd(&sm[c + j], dg_acc[i][j]); atomicAdd(&sm[cols + c + j], db_acc[i][j]); }
+      *reinterpret_cast<float4*>(mine + c) = make_float4(dg_acc[i][0], dg_acc[i][1], dg_acc[i][2], dg_acc[i][3]);
+      *reinterpret_cast<float4*>(mine + cols + c) = make_float4(db_acc[i][0], db_acc[i][1], db_acc[i][2], db_acc[i][3]);
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    if (dgamma) atomicAdd(&dgamma[c], sm[c]);
-    if (dbeta) atomicAdd(&dbeta[c], sm[cols + c]);
+  // one 16-byte vector reduction per 4 columns per block (4x fewer same-address L2 atomics than scalar atomicAdd)
+  for (int v = threadIdx.x; v < 2 * (cols / 4); v += blockDim.x) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < nwarps; ++w) {
+      const float4 t = *reinterpret_cast<const float4*>(sm + (size_t)w * 2 * cols + 4 * v);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    float* dst = (4 * v < cols) ? (dgamma ? dgamma + 4 * v : nullptr) : (dbeta ? dbeta + (4 * v - cols) : nullptr);
+    if (dst) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
   }
 }
 
@@ -309,11 +314,11 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
                    ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0);
 #define LN_BWD_VEC(NV)                                                                                                  \
   DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
-      (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV>, grid, 256, smem, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
+      (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV>, grid, 256, smem * 8, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
                                                                    (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
-  if (vec && cols <= 256) LN_BWD_VEC(2);
-  else if (vec && cols <= 512) LN_BWD_VEC(4);
-  else if (vec) LN_BWD_VEC(8);
+  const bool vec_ok = vec && ((reinterpret_cast<uintptr_t>(dgamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dbeta) & 15) == 0);
+  if (vec_ok && cols <= 256) LN_BWD_VEC(2);
+  else if (vec_ok && cols <= 512) LN_BWD_VEC(4);      // 8 warps x 2 x 512 floats = 32 KB of per-warp partials
   else if (cols <= 256) LN_BWD_LAUNCH(8);
   else if (cols <= 512) LN_BWD_LAUNCH(16);
   else LN_BWD_LAUNCH(32);
