@@ -220,13 +220,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 }
 
 // vector variant: cols % 4 == 0, lane owns NV groups of 4 contiguous columns
-template <typename TDY, typename TX, typename TDX, int NV>
-__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
+template <typename TDY, typename TX, typename TDX, int NV, int R>
+__global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ dres, TDX* __restrict__ dx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
-                                                          int cols, int relu) {
+                                                          int cols, int relu, void* __restrict__ dnext, int dnext_bf16,
+                                                          const DropoutSpec ndrop) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];   // [nwarps][2][cols] per-warp partials (no shared-memory atomics)
@@ -239,40 +240,79 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__
     for (int j = 0; j < 4; ++j) { gam[i][j] = 0.f; bet[i][j] = 0.f; dg_acc[i][j] = 0.f; db_acc[i][j] = 0.f; }
     if (c < cols) { load4<float>(gamma + c, gam[i]); load4<float>(beta + c, bet[i]); }
   }
+  // R rows per warp iteration with every global load (x, dy, residual gradient, statistics) issued up front: with a few
+  // rows per warp the kernel is bound by bytes in flight (Little's law), not by bandwidth
+  const uint32_t nthresh = dropout_thresh16(ndrop.p);
   const int64_t warps_total = (int64_t)gridDim.x * nwarps;
-  for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += warps_total) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NV][4], d[NV][4];
-    float c1 = 0.f, c2 = 0.f;
+  for (int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * R; row0 < rows; row0 += warps_total * R) {
+    float xh[R][NV][4], d[R][NV][4], rr[R][NV][4], mu[R], rs[R];
+    uint32_t kb[R][NV];          // keep-bits of the NEXT block's post-dropout for this lane's 4-column groups (dnext only)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = 4 * lane + 128 * i;
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      const bool rv = row < rows;
+      mu[r] = rv ? mean[row] : 0.f; rs[r] = rv ? rstd[row] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { xh[i][j] = 0.f; d[i][j] = 0.f; }
-      if (c < cols) {
-        load4<TX>(x + row * cols + c, xh[i]);
-        load4<TDY>(dy + row * cols + c, d[i]);
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          xh[i][j] = (xh[i][j] - mu) * rs;
-          if (relu && (xh[i][j] * gam[i][j] + bet[i][j]) <= 0.f) d[i][j] = 0.f;
-          const float g = d[i][j] * gam[i][j];
-          c1 += g; c2 += g * xh[i][j];
-          dg_acc[i][j] += d[i][j] * xh[i][j]; db_acc[i][j] += d[i][j];
+        for (int j = 0; j < 4; ++j) { xh[r][i][j] = 0.f; d[r][i][j] = 0.f; rr[r][i][j] = 0.f; }
+        if (rv && c < cols) {
+          load4<TX>(x + row * cols + c, xh[r][i]);
+          load4<TDY>(dy + row * cols + c, d[r][i]);
+          if (dres) load4<float>(dres + row * cols + c, rr[r][i]);
+          kb[r][i] = 0xffu;
+          if (dnext && ndrop.p > 0.f) kb[r][i] = drop_keep8(ndrop, (uint64_t)(row * cols + c) >> 3, nthresh) >> (c & 4);
         }
       }
     }
-    c1 = warp_sum(c1) / cols; c2 = warp_sum(c2) / cols;
+    float c1[R], c2[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = 4 * lane + 128 * i;
-      if (c < cols) {
-        float o[4];
-        float r[4] = {0.f, 0.f, 0.f, 0.f};
-        if (dres) load4<float>(dres + row * cols + c, r);
+    for (int r = 0; r < R; ++r) {
+      c1[r] = 0.f; c2[r] = 0.f;
+      const bool rv = row0 + r < rows;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = rs * (d[i][j] * gam[i][j] - c1 - xh[i][j] * c2) + r[j];
-        store4<TDX>(dx + row * cols + c, o);
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (rv && c < cols) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            xh[r][i][j] = (xh[r][i][j] - mu[r]) * rs[r];
+            if (relu && (xh[r][i][j] * gam[i][j] + bet[i][j]) <= 0.f) d[r][i][j] = 0.f;
+            const float g = d[r][i][j] * gam[i][j];
+            c1[r] += g; c2[r] += g * xh[r][i][j];
+            dg_acc[i][j] += d[r][i][j] * xh[r][i][j]; db_acc[i][j] += d[r][i][j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) { c1[r] += __shfl_xor_sync(0xffffffffu, c1[r], o); c2[r] += __shfl_xor_sync(0xffffffffu, c2[r], o); }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) continue;
+      const float m1 = c1[r] / cols, m2 = c2[r] / cols;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < cols) {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = rs[r] * (d[r][i][j] * gam[i][j] - m1 - xh[r][i][j] * m2) + rr[r][i][j];
+          store4<TDX>(dx + row * cols + c, o);
+          if (dnext) {
+            // the consumer block's first op fused here: dY = cast(dropout'(dx)) in the activation dtype
+            const float nscale = ndrop.p > 0.f ? ndrop.scale : 1.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = ((kb[r][i] >> j) & 1u) ? o[j] * nscale : 0.f;
+            if (dnext_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dnext) + row * cols + c, o);
+            else store4<float>(reinterpret_cast<float*>(dnext) + row * cols + c, o);
+          }
+        }
       }
     }
   }
@@ -301,9 +341,19 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const TDY* __restrict__
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
                   float* dbeta, int64_t rows, int cols, int relu, cudaStream_t s) {
+  return layernorm_bwd_next(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, beta, dres, dx, dx_dtype, dgamma, dbeta, rows, cols, relu,
+                            nullptr, F32, no_dropout(), s);
+}
+
+// Same, plus (dnext != null) dnext = cast(dropout'(dx)) in `dnext_dtype` with the NEXT backward block's post-dropout
+// site — that block's first kernel, fused into this one.
+int layernorm_bwd_next(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
+                       float* dbeta, int64_t rows, int cols, int relu, void* dnext, int dnext_dtype, DropoutSpec ndrop,
+                       cudaStream_t s) {
   if (rows == 0) return 0;
   B200ST_CHECK(cols <= 1024, "layernorm_bwd supports cols <= 1024");
-  const int grid = grid_for(rows, 8 * 4, 148 * 8);      // ~4 rows per warp, up to 8 blocks per SM
+  const int grid = grid_for(rows, 8 * 2, 148 * 8);      // 2 rows in flight per warp; long inputs loop
   const size_t smem = 2 * (size_t)cols * sizeof(float);
 #define LN_BWD_LAUNCH(CPL)                                                                                              \
   DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
@@ -312,13 +362,16 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
   const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0);
-#define LN_BWD_VEC(NV)                                                                                                  \
+#define LN_BWD_VEC(NV, RR)                                                                                                \
   DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
-      (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV>, grid, 256, smem * 8, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
-                                                                   (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
+      (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV, RR>, grid, 256, smem * 8, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
+                                                                   (TDX*)dx, dgamma, dbeta, rows, cols, relu, fused_next ? dnext : nullptr, dnext_dtype == BF16 ? 1 : 0, ndrop)))))
   const bool vec_ok = vec && ((reinterpret_cast<uintptr_t>(dgamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dbeta) & 15) == 0);
-  if (vec_ok && cols <= 256) LN_BWD_VEC(2);
-  else if (vec_ok && cols <= 512) LN_BWD_VEC(4);      // 8 warps x 2 x 512 floats = 32 KB of per-warp partials
+  const bool fused_next = dnext && vec_ok && cols <= 512 && ((reinterpret_cast<uintptr_t>(dnext) & 15) == 0);
+  // short inputs (a few rows per warp) are bound by bytes in flight: 2 rows per warp iteration; long ones by occupancy
+  if (vec_ok && cols <= 256 && rows <= 65536) LN_BWD_VEC(2, 2);
+  else if (vec_ok && cols <= 256) LN_BWD_VEC(2, 1);
+  else if (vec_ok && cols <= 512) LN_BWD_VEC(4, 1);      // 8 warps x 2 x 512 floats = 32 KB of per-warp partials
   else if (cols <= 256) LN_BWD_LAUNCH(8);
   else if (cols <= 512) LN_BWD_LAUNCH(16);
   else LN_BWD_LAUNCH(32);
@@ -326,6 +379,10 @@ int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
 #undef LN_BWD_LAUNCH
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
+  if (dnext && !fused_next) {         // shapes outside the vector kernel: the separate kernel the fusion replaces
+    B200ST_CHECK(dx_dtype == F32, "layernorm_bwd_next fallback needs an fp32 dx");
+    B200ST_TRY(cast_dropout(reinterpret_cast<const float*>(dx), dnext, dnext_dtype, rows * cols, ndrop, s));
+  }
   return 0;
 }
 

@@ -17,6 +17,11 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
                   float* dbeta, int64_t rows, int cols, int relu, cudaStream_t s);
+// + dnext = cast(dropout'(dx)) for the next backward block (its first kernel fused into this one)
+int layernorm_bwd_next(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,
+                       float* dbeta, int64_t rows, int cols, int relu, void* dnext, int dnext_dtype, DropoutSpec ndrop,
+                       cudaStream_t s);
 
 // P = softmax(S + bias[b, k] + causal) over k (multi_head_attention.py:147-160,207-208).
 // S fp32 [B,H,Tq,ldS]; bias fp32 [B,Tk] or null; causal: key k visible to query q iff k <= q + (Tk - Tq).

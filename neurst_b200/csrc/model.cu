@@ -192,6 +192,19 @@ struct Ctx {
     if (cudaEventRecord(side->done[cur_par], s) != cudaSuccess) launch_failed = true;
     side_pending[cur_par] = true;
   }
+  // Fused hand-over between backward blocks: the final LayerNorm-backward of a block also writes the NEXT block's
+  // dY = cast(dropout'(dx)) into that block's parity buffer (set by the stack loop through `next_drop`).
+  const DropoutSpec* next_drop = nullptr;   // post-dropout site of the block that runs next (null: no fused hand-over)
+  bool dy_ready = false;                    // the previous block already produced this block's dY
+  // parity the next block will select; its side-stream readers (two blocks ago) must be done before it is overwritten
+  int next_parity_ready() {
+    const int par = bwd_blocks & 1;
+    if (side && !dry && side_pending[par]) {
+      if (cudaStreamWaitEvent(st, side->done[par], 0) != cudaSuccess) launch_failed = true;
+      side_pending[par] = false;
+    }
+    return par;
+  }
   void join_side() {
     if (!side || dry) return;
     for (int i = 0; i < 2; ++i)
@@ -272,6 +285,11 @@ static int need_param(const Ctx& c, const std::string& n) {
   if (!c.info(n)) B200ST_FAIL("parameter '" + n + "' not in this model");
   return 0;
 }
+
+struct Scratch;
+// final LayerNorm-backward of a block (+ fused production of the next block's dY when the stack loop announced one)
+static int block_ln_bwd(Ctx& c, Scratch& sc, const float* dh, const float* x_in, const float* mean, const float* rstd,
+                        const std::string& pre, const float* dx_out, float* dx_in, int M, int d);
 
 // ---- dense layers:  weights stored [K_in, N_out] (TF layout) -----------------------------------
 // Y[M,N] = epi(X[M,K] W)
@@ -440,6 +458,21 @@ struct Scratch {   // shared transient buffers (sized for the largest sublayer)
   float* dq32 = nullptr;    // [M,d] fp32 (fused attention: dQ reduction across kv blocks)
 };
 
+static int block_ln_bwd(Ctx& c, Scratch& sc, const float* dh, const float* x_in, const float* mean, const float* rstd,
+                        const std::string& pre, const float* dx_out, float* dx_in, int M, int d) {
+  void* dnext = nullptr;
+  DropoutSpec nd = no_dropout();
+  if (c.next_drop) {
+    dnext = sc.dY2[c.next_parity_ready()];
+    nd = *c.next_drop;
+    c.next_drop = nullptr;
+    c.dy_ready = true;
+  }
+  RUN(layernorm_bwd_next(dh, F32, x_in, F32, mean, rstd, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), dx_out, dx_in, F32,
+                         c.G(pre + ".ln.gamma"), c.G(pre + ".ln.beta"), M, d, 0, dnext, c.adt, nd, c.st));
+  return 0;
+}
+
 // x_out = x_in + dropout(Attn(LN(x_in)))  — pre-norm block (common_layers.py:73-85)
 static int self_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_in, float* x_out, int B, int T, const float* bias,
                                int causal, Scratch& sc, AttnSave& sv) {
@@ -476,7 +509,8 @@ static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_o
   sc.select(c.begin_bwd_block());
   const Config& cf = c.m.cfg;
   const int d = cf.d, M = sv.dims.B * sv.dims.Tq;
-  RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
+  if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
+  else RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
   B200ST_TRY(linear_wgrad(c, sv.ctx, d, sc.dY, d, M, d, d, pre + ".out.kernel", pre + ".out.bias"));
   GemmEpilogue e0 = gemm_defaults().epi;
   B200ST_TRY(linear_dgrad(c, sc.dY, d, M, d, d, pre + ".out.kernel", e0, sc.dctx, c.adt, d));
@@ -486,8 +520,7 @@ static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_o
                            dq, dk, dv, sv.ctx, sv.lse, sv.bias, sv.causal, sc.dq32));
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, 3 * d, M, d, 3 * d, pre + ".qkv.kernel", pre + ".qkv.bias"));
   B200ST_TRY(linear_dgrad(c, sc.dqkv, 3 * d, M, 3 * d, d, pre + ".qkv.kernel", e0, sc.dh, F32, d));
-  RUN(layernorm_bwd(sc.dh, F32, sv.x_in, F32, sv.mean, sv.rstd, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), dx_out, dx_in, F32,
-                    c.G(pre + ".ln.gamma"), c.G(pre + ".ln.beta"), M, d, 0, c.st));
+  B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
   return 0;
 }
 
@@ -530,7 +563,8 @@ static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_
   sc.select(c.begin_bwd_block());
   const Config& cf = c.m.cfg;
   const int d = cf.d, M = sv.dims.B * sv.dims.Tq, Mk = sv.dims.B * sv.dims.Tk;
-  RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
+  if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
+  else RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
   B200ST_TRY(linear_wgrad(c, sv.ctx, d, sc.dY, d, M, d, d, pre + ".out.kernel", pre + ".out.bias"));
   GemmEpilogue e0 = gemm_defaults().epi;
   B200ST_TRY(linear_dgrad(c, sc.dY, d, M, d, d, pre + ".out.kernel", e0, sc.dctx, c.adt, d));
@@ -540,8 +574,7 @@ static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_
                            dq, dk, dv, sv.ctx, sv.lse, sv.bias, 0, sc.dq32));
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, d, M, d, d, pre + ".q.kernel", pre + ".q.bias"));
   B200ST_TRY(linear_dgrad(c, sc.dqkv, d, M, d, d, pre + ".q.kernel", e0, sc.dh, F32, d));
-  RUN(layernorm_bwd(sc.dh, F32, sv.x_in, F32, sv.mean, sv.rstd, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), dx_out, dx_in, F32,
-                    c.G(pre + ".ln.gamma"), c.G(pre + ".ln.beta"), M, d, 0, c.st));
+  B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
   B200ST_TRY(linear_wgrad(c, sv.mem, d, sc.dkv, 2 * d, Mk, d, 2 * d, pre + ".kv.kernel", pre + ".kv.bias"));
   GemmEpilogue ea = gemm_defaults().epi;
   ea.accumulate = 1;                              // memory gradient accumulates over decoder layers
@@ -574,7 +607,8 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
   sc.select(c.begin_bwd_block());
   const Config& cf = c.m.cfg;
   const int d = cf.d, f = cf.ffn, M = sv.M;
-  RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
+  if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
+  else RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
   B200ST_TRY(linear_wgrad(c, sv.f1, f, sc.dY, d, M, f, d, pre + ".w2", pre + ".b2"));
   GemmEpilogue e1 = gemm_defaults().epi;
   e1.mask_src = sv.f1; e1.mask_dtype = c.adt; e1.mask_ld = f;      // relu' and ffn-dropout mask: stored f1 > 0
@@ -584,8 +618,7 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dF1, f, M, d, f, pre + ".w1", pre + ".b1"));
   GemmEpilogue e0 = gemm_defaults().epi;
   B200ST_TRY(linear_dgrad(c, sc.dF1, f, M, f, d, pre + ".w1", e0, sc.dh, F32, d));
-  RUN(layernorm_bwd(sc.dh, F32, sv.x_in, F32, sv.mean, sv.rstd, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), dx_out, dx_in, F32,
-                    c.G(pre + ".ln.gamma"), c.G(pre + ".ln.beta"), M, d, 0, c.st));
+  B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
   return 0;
 }
 
@@ -647,7 +680,12 @@ static int encoder_bwd(Ctx& c, const float* d_out, float* dx, float* dx_tmp, Scr
                     c.G("enc.out_ln.gamma"), c.G("enc.out_ln.beta"), M, d, 0, c.st));
   for (int i = cf.enc_layers - 1; i >= 0; --i) {
     const std::string p = "enc." + std::to_string(i);
+    // each block's LayerNorm-backward also emits the next block's dY = cast(dropout'(dx)) (same M for the whole stack)
+    const DropoutSpec nd_att = c.drop(cf.postprocess_dropout, sv.att[i].s_post);
+    c.next_drop = &nd_att;
     B200ST_TRY(ffn_block_bwd(c, p + ".ffn", dx, dx_tmp, sc, sv.ffn[i]));
+    DropoutSpec nd_ffn = no_dropout();
+    if (i > 0) { nd_ffn = c.drop(cf.postprocess_dropout, sv.ffn[i - 1].s_post); c.next_drop = &nd_ffn; }
     B200ST_TRY(self_attn_block_bwd(c, p + ".att", dx_tmp, dx, sc, sv.att[i]));
   }
   return 0;
@@ -698,12 +736,19 @@ static int decoder_bwd(Ctx& c, const float* d_out, float* dx, float* dx_tmp, flo
   float* a = dx; float* b = dx_tmp;
   for (int i = cf.dec_layers - 1; i >= 0; --i) {
     const std::string p = "dec." + std::to_string(i);
+    const bool cross = cf.with_cross_attention && has_mem;
+    const DropoutSpec nd1 = c.drop(cf.postprocess_dropout, cross ? sv.cross[i].s_post : sv.self[i].s_post);
+    c.next_drop = &nd1;
     B200ST_TRY(ffn_block_bwd(c, p + ".ffn", a, b, sc, sv.ffn[i]));
     std::swap(a, b);
-    if (cf.with_cross_attention && has_mem) {
+    if (cross) {
+      const DropoutSpec nd2 = c.drop(cf.postprocess_dropout, sv.self[i].s_post);
+      c.next_drop = &nd2;
       B200ST_TRY(cross_attn_block_bwd(c, p + ".cross", a, b, dmem, sc, sv.cross[i]));
       std::swap(a, b);
     }
+    DropoutSpec nd3 = no_dropout();
+    if (i > 0) { nd3 = c.drop(cf.postprocess_dropout, sv.ffn[i - 1].s_post); c.next_drop = &nd3; }
     B200ST_TRY(self_attn_block_bwd(c, p + ".self", a, b, sc, sv.self[i]));
     std::swap(a, b);
   }
