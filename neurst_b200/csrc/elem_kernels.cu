@@ -867,6 +867,74 @@ __global__ void __launch_bounds__(256) lsce_kernel(const float* __restrict__ log
   }
 }
 
+// Row held in registers (V <= 1024 * NV, V % 4 == 0): the fp32 logits are read from HBM exactly once.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) lsce_vec_kernel(const float* __restrict__ logits, const int64_t* __restrict__ trg,
+                                                        const int64_t* __restrict__ trg_length, int B, int L, int V,
+                                                        float eps_ls, float* __restrict__ nll_sum, T* __restrict__ dlogits,
+                                                        float loss_scale) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float sm[32];
+  const int64_t row = blockIdx.x;
+  const int b = (int)(row / L), l = (int)(row % L);
+  const float w = (l < trg_length[b]) ? 1.f : 0.f;
+  float tok = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { int64_t len = trg_length[i]; tok += (float)(len < L ? (len < 0 ? 0 : len) : L); }
+  const float total_tokens = block_reduce(tok, sm, false);
+  const float* z = logits + row * V;
+  float4 r[NV];
+  float mx = -INFINITY, sz = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = 4 * (threadIdx.x + 256 * i);
+    if (v < V) {
+      r[i] = __ldg(reinterpret_cast<const float4*>(z + v));
+      mx = fmaxf(fmaxf(mx, fmaxf(r[i].x, r[i].y)), fmaxf(r[i].z, r[i].w));
+      sz += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+    }
+  }
+  mx = block_reduce(mx, sm, true);
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = 4 * (threadIdx.x + 256 * i);
+    if (v < V) {
+      r[i].x = expf(r[i].x - mx); r[i].y = expf(r[i].y - mx); r[i].z = expf(r[i].z - mx); r[i].w = expf(r[i].w - mx);
+      se += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+    }
+  }
+  se = block_reduce(se, sm, false);
+  sz = block_reduce(sz, sm, false);
+  const float lse = mx + logf(se);
+  int64_t label = trg[row];
+  label = label < 0 ? 0 : (label >= V ? V - 1 : label);
+  const float conf = 1.f - eps_ls;
+  const float low = eps_ls / (float)(V - 1);
+  if (threadIdx.x == 0) {
+    const float lp_label = z[label] - lse;
+    const float sum_lp = sz - (float)V * lse;
+    float xent = -((conf - low) * lp_label + low * sum_lp);
+    if (eps_ls > 0.f) xent -= -(conf * logf(conf) + (float)(V - 1) * low * logf(low + 1e-20f));
+    atomicAdd(&nll_sum[b], xent * w);
+  }
+  if (dlogits) {
+    const float coef = (total_tokens > 0.f) ? w * loss_scale / total_tokens : 0.f;
+    const float inv_se = 1.0f / se;
+    T* dz = dlogits + row * V;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = 4 * (threadIdx.x + 256 * i);
+      if (v < V) {
+        float o[4] = {r[i].x * inv_se, r[i].y * inv_se, r[i].z * inv_se, r[i].w * inv_se};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = coef * (o[j] - ((v + j) == label ? conf : low));
+        store4<T>(dz + v, o);
+      }
+    }
+  }
+}
+
 __global__ void lsce_finalize_kernel(const float* __restrict__ nll_sum, const int64_t* __restrict__ trg_length, int B, int L,
                                      float* __restrict__ n_tokens, float* __restrict__ loss) {
   pdl_wait();
@@ -889,8 +957,16 @@ int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_len
                  float loss_scale, cudaStream_t s) {
   if (B * L == 0) return 0;
   B200ST_CUDA(cudaMemsetAsync(nll_sum, 0, sizeof(float) * B, s));
-  DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_kernel<T>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing, nll_sum,
-                                                                    (T*)dlogits, loss_scale)));
+  const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) && (!dlogits || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0);
+  if (vec && V <= 8192)
+    DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_vec_kernel<T, 8>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing,
+                                           nll_sum, (T*)dlogits, loss_scale)));
+  else if (vec && V <= 32768)
+    DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_vec_kernel<T, 32>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing,
+                                           nll_sum, (T*)dlogits, loss_scale)));
+  else
+    DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_kernel<T>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing, nll_sum,
+                                           (T*)dlogits, loss_scale)));
   B200ST_LAUNCH_CHECK();
   launch_pdl(lsce_finalize_kernel, 1, 256, 0, s, nll_sum, trg_length, B, L, n_tokens, loss);
   g_kernel_launches += 2;
