@@ -977,12 +977,37 @@ int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_len
 // =============================================================================================
 // optimizer / parameter utilities
 // =============================================================================================
-__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, float b1, float b2, float eps,
                             float gscale, int zero_grad) {
   pdl_wait();
   pdl_trigger();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // 16-byte accesses (all arenas are 256-byte aligned); scalar tail for n % 4
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i], m4 = reinterpret_cast<const float4*>(m)[i];
+    const float4 v4 = reinterpret_cast<const float4*>(v)[i], p4 = reinterpret_cast<const float4*>(p)[i];
+    const float gi[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+    const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w}, po[4] = {p4.x, p4.y, p4.z, p4.w};
+    float mi[4], vi[4], pi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mi[j] = b1 * mo[j] + (1.f - b1) * gi[j];
+      vi[j] = b2 * vo[j] + (1.f - b2) * gi[j] * gi[j];
+      pi[j] = po[j] - lr_t * mi[j] / (sqrtf(vi[j]) + eps);
+    }
+    reinterpret_cast<float4*>(m)[i] = make_float4(mi[0], mi[1], mi[2], mi[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vi[0], vi[1], vi[2], vi[3]);
+    reinterpret_cast<float4*>(p)[i] = make_float4(pi[0], pi[1], pi[2], pi[3]);
+    if (shadow) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(pi[0], pi[1]), h1 = __floats2bfloat162_rn(pi[2], pi[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(shadow)[i] = pk;
+    }
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -995,7 +1020,9 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
 int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
               float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s) {
   if (n == 0) return 0;
-  launch_pdl(adam_kernel, grid_for(n, 256 * 4), 256, 0, s, p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
+  B200ST_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(shadow) & 7) == 0, "adam: arenas must be 16-byte aligned");
+  launch_pdl(adam_kernel, grid_for(n, 256 * 4 * 4), 256, 0, s, p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

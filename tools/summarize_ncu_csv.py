@@ -2,7 +2,7 @@
 
 usage: summarize_ncu_csv.py launches.csv [--json out.json --match tc_gemm_kernel]
 Prints per-kernel launch count, total / average gpu__time_duration and (when captured) DRAM bytes; with --json writes
-{"launches", "dram_bytes_per_step", "time_us"} for the kernels whose name contains --match."""
+{"launches", "dram_bytes_total", "time_us"} for the kernels whose name contains --match."""
 import csv, collections, json, re, sys
 path = sys.argv[1]
 match = sys.argv[sys.argv.index("--match") + 1] if "--match" in sys.argv else None
@@ -34,4 +34,4 @@ for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 if out_json and match:
     sel = [(n, t, b) for k, (n, t, b) in agg.items() if match in k]
     json.dump({"kernel": match, "launches": sum(x[0] for x in sel), "time_us": sum(x[1] for x in sel),
-               "dram_bytes_per_step": sum(x[2] for x in sel), "source": path}, open(out_json, "w"), indent=1)
+               "dram_bytes_total": sum(x[2] for x in sel), "source": path}, open(out_json, "w"), indent=1)
