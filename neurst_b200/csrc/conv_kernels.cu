@@ -718,6 +718,47 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ y1, T
   }
 }
 
+
+// Production shape (one 16-byte vector per lane and row, i.e. C * sizeof(T) == 512): one warp per OUTPUT row, the
+// position is decoded once and the 9 tap loads are all in flight before the 9 stores (the generic kernel spends more
+// instructions on index arithmetic than on the copy).
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_row_kernel(const T* __restrict__ y1, T* __restrict__ col, int B, int T1, int F1,
+                                                          int T2, int F2, const T* __restrict__ gamma, const T* __restrict__ beta) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int EPV = 16 / sizeof(T);
+  constexpr int C = 32 * EPV;
+  const int lane = threadIdx.x & 31;
+  const int64_t nrows = (int64_t)B * T2 * F2;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  AffineRegs<T> ar;
+  if (gamma) ar.load(gamma, beta, lane * EPV);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += warps_total) {
+    const int f2 = (int)(row % F2);
+    const int t2 = (int)((row / F2) % T2);
+    const int b = (int)(row / ((int64_t)F2 * T2));
+    const T* base = y1 + ((int64_t)b * T1 * F1) * C + lane * EPV;
+    uint4 v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int t = 2 * t2 + tap / 3 - 1, f = 2 * f2 + tap % 3 - 1;
+      const bool inside = t >= 0 && t < T1 && f >= 0 && f < F1;
+      v[tap] = make_uint4(0, 0, 0, 0);
+      if (inside) v[tap] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)t * F1 + f) * C));
+    }
+    T* dst = col + row * 9 * C + lane * EPV;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int t = 2 * t2 + tap / 3 - 1, f = 2 * f2 + tap % 3 - 1;
+      const bool inside = t >= 0 && t < T1 && f >= 0 && f < F1;
+      uint4 o = v[tap];
+      if (gamma && inside) o = affine_relu_vec(o, ar.g, ar.b);
+      *reinterpret_cast<uint4*>(dst + tap * C) = o;
+    }
+  }
+}
+
 }  // namespace
 
 static int pick_grid(int64_t npos, int per_block, int cap) {
@@ -840,7 +881,10 @@ int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int
   const bool vec = ((C * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
   const bool one = vec && C * esz == 32 * 16;
-  if (one) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true, true>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, (const TT*)gamma, (const TT*)beta)));
+  if (one) {
+    const int grid_r = pick_grid(nchunks / 9, 8 * 4, 148 * 8);
+    DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_row_kernel<TT>, grid_r, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, T2, F2, (const TT*)gamma, (const TT*)beta)));
+  }
   else if (vec) DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, true, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, (const TT*)gamma, (const TT*)beta)));
   else DISPATCH_DTYPE(dtype, TT, (launch_pdl(im2col_kernel<TT, false, false>, grid, 256, 0, s, (const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2, (const TT*)gamma, (const TT*)beta)));
   ++g_kernel_launches;

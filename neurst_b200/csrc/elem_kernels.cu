@@ -1049,16 +1049,32 @@ __global__ void __launch_bounds__(256) dropout_bits_multi_kernel(const DropBitsT
   pdl_trigger();
   const uint64_t sd = seed_ptr ? *seed_ptr : seed;
   const int64_t total = t.goff[t.n];
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-    int lo = 0, hi = t.n - 1;                      // last site whose first group <= g
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (t.goff[mid] <= g) lo = mid; else hi = mid - 1; }
-    const int64_t local = g - t.goff[lo];
-    base[t.boff[lo] + local] = (uint8_t)dropout_keep8(sd, t.stream[lo], (uint64_t)local, t.thresh[lo]);
+  // 4 consecutive groups (= 4 output bytes) per thread: one site lookup and one 32-bit store when the 4 groups lie in one
+  // site and the destination is 4-byte aligned (site byte offsets are 256-byte aligned, so this is the common case)
+  const int64_t total4 = (total + 3) >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g0 = q << 2;
+    int lo = 0, hi = t.n - 1;                      // last site whose first group <= g0
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (t.goff[mid] <= g0) lo = mid; else hi = mid - 1; }
+    const int64_t local = g0 - t.goff[lo];
+    if (g0 + 3 < t.goff[lo + 1] && ((t.boff[lo] + local) & 3) == 0) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w |= dropout_keep8(sd, t.stream[lo], (uint64_t)(local + j), t.thresh[lo]) << (8 * j);
+      *reinterpret_cast<uint32_t*>(base + t.boff[lo] + local) = w;
+    } else {
+      for (int64_t g = g0; g < g0 + 4 && g < total; ++g) {
+        int l2 = lo;
+        while (l2 + 1 < t.n && t.goff[l2 + 1] <= g) ++l2;
+        const int64_t loc = g - t.goff[l2];
+        base[t.boff[l2] + loc] = (uint8_t)dropout_keep8(sd, t.stream[l2], (uint64_t)loc, t.thresh[l2]);
+      }
+    }
   }
 }
 int dropout_bits_multi(const DropBitsTable& t, uint64_t seed, const uint64_t* seed_ptr, uint8_t* base, cudaStream_t s) {
   if (t.n == 0 || t.goff[t.n] == 0) return 0;
-  launch_pdl(dropout_bits_multi_kernel, grid_for(t.goff[t.n], 256, 148 * 8), 256, 0, s, t, seed, seed_ptr, base);
+  launch_pdl(dropout_bits_multi_kernel, grid_for((t.goff[t.n] + 3) / 4, 256, 148 * 8), 256, 0, s, t, seed, seed_ptr, base);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;
