@@ -88,10 +88,19 @@ __device__ __forceinline__ void load_keep64(const DropoutSpec& d, bool row_ok, i
     }
     return;
   }
+  if (d.bits) {                           // bitmap, unaligned rows: 8 byte loads (all issued before the first use)
+    uint32_t byte[8];
+    const uint8_t* bp = d.bits + ((uint64_t)(row_bit0 + k0) >> 3);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 8; ++g) byte[g] = (k0 + 8 * g < Tkp) ? (uint32_t)__ldg(bp + g) : 0xffu;
+    keep[0] = byte[0] | (byte[1] << 8) | (byte[2] << 16) | (byte[3] << 24);
+    keep[1] = byte[4] | (byte[5] << 8) | (byte[6] << 16) | (byte[7] << 24);
+    return;
+  }
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {           // no bitmap: regenerate with Philox (stand-alone attention API)
     if (k0 + 8 * g < Tkp) {
-      const uint32_t byte = drop_keep8(d, (uint64_t)(row_bit0 + k0 + 8 * g) >> 3, thresh);
+      const uint32_t byte = dropout_keep8(dropout_seed(d), d.stream, (uint64_t)(row_bit0 + k0 + 8 * g) >> 3, thresh);
       keep[g >> 2] = (keep[g >> 2] & ~(0xffu << (8 * (g & 3)))) | (byte << (8 * (g & 3)));
     }
   }

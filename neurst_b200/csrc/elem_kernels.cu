@@ -242,7 +242,6 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const TDY* __restric
   }
   // R rows per warp iteration with every global load (x, dy, residual gradient, statistics) issued up front: with a few
   // rows per warp the kernel is bound by bytes in flight (Little's law), not by bandwidth
-  const uint32_t nthresh = dropout_thresh16(ndrop.p);
   const int64_t warps_total = (int64_t)gridDim.x * nwarps;
   for (int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * R; row0 < rows; row0 += warps_total * R) {
     float xh[R][NV][4], d[R][NV][4], rr[R][NV][4], mu[R], rs[R];
@@ -262,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const TDY* __restric
           load4<TDY>(dy + row * cols + c, d[r][i]);
           if (dres) load4<float>(dres + row * cols + c, rr[r][i]);
           kb[r][i] = 0xffu;
-          if (dnext && ndrop.p > 0.f) kb[r][i] = drop_keep8(ndrop, (uint64_t)(row * cols + c) >> 3, nthresh) >> (c & 4);
+          if (dnext && ndrop.bits) kb[r][i] = __ldg(ndrop.bits + ((uint64_t)(row * cols + c) >> 3));   // bitmap only (host guarantees); raw byte, used after the math
         }
       }
     }
@@ -308,7 +307,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const TDY* __restric
             // the consumer block's first op fused here: dY = cast(dropout'(dx)) in the activation dtype
             const float nscale = ndrop.p > 0.f ? ndrop.scale : 1.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = ((kb[r][i] >> j) & 1u) ? o[j] * nscale : 0.f;
+            for (int j = 0; j < 4; ++j) o[j] = ((kb[r][i] >> ((c & 4) + j)) & 1u) ? o[j] * nscale : 0.f;
             if (dnext_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dnext) + row * cols + c, o);
             else store4<float>(reinterpret_cast<float*>(dnext) + row * cols + c, o);
           }
@@ -367,7 +366,8 @@ int layernorm_bwd_next(const void* dy, int dy_dtype, const void* x, int x_dtype,
       (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV, RR>, grid, 256, smem * 8, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
                                                                    (TDX*)dx, dgamma, dbeta, rows, cols, relu, fused_next ? dnext : nullptr, dnext_dtype == BF16 ? 1 : 0, ndrop)))))
   const bool vec_ok = vec && ((reinterpret_cast<uintptr_t>(dgamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dbeta) & 15) == 0);
-  const bool fused_next = dnext && vec_ok && cols <= 512 && ((reinterpret_cast<uintptr_t>(dnext) & 15) == 0);
+  const bool fused_next = dnext && vec_ok && cols <= 512 && ((reinterpret_cast<uintptr_t>(dnext) & 15) == 0) &&
+                          (ndrop.p <= 0.f || ndrop.bits != nullptr);      // on-the-fly Philox sites use the separate kernel
   // short inputs (a few rows per warp) are bound by bytes in flight: 2 rows per warp iteration; long ones by occupancy
   if (vec_ok && cols <= 256 && rows <= 65536) LN_BWD_VEC(2, 2);
   else if (vec_ok && cols <= 256) LN_BWD_VEC(2, 1);
