@@ -299,10 +299,13 @@ def run_gpu(args):
     torch.cuda.synchronize()
     lib.profile_begin()
     trainer.use_cuda_graph = False          # eager launches so each GEMM can be bracketed by events
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
     resident_step(0)
+    pe1.record()
     torch.cuda.synchronize()
     gms, gfl, gn = lib.profile_end()
-    gemm = dict(ms=gms, flops=gfl, launches=gn)
+    gemm = dict(ms=gms, flops=gfl, launches=gn, step_ms=pe0.elapsed_time(pe1))   # same (eager, single-stream) step
     barrier()
     # kernels per step: counted on one eagerly launched step (a CUDA-graph replay re-issues the same kernel nodes)
     trainer.use_cuda_graph = False
@@ -350,11 +353,12 @@ def run_gpu(args):
     # (profiles/r01_gemm_traffic.json, same command), averaged like `achieved`.
     step_rf = {"achieved": ach, "frac": ach / peaks["tflops_sustained"], "algorithmic_flops_per_step": fl,
                "mflop_per_frame": fl / (B * T) / 1e6, "note": "all kernels of the step / step time"}
-    traffic = None
+    traffic, ncu_share = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_total"] / max(1, tj["launches"])
+        ncu_share = tj.get("share_of_step")
     except Exception:
         pass
     if gemm and gemm["ms"] > 0:
@@ -364,7 +368,9 @@ def run_gpu(args):
                             "traffic": traffic, "peak_source": peaks["source"], "launches_per_step": gemm["launches"],
                             "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
                             "algorithmic_flops_per_launch": gemm["flops"] / max(1, gemm["launches"]),
-                            "share_of_step": gemm["ms"] / ms_step, "step": step_rf}
+                            "share_of_step": gemm["ms"] / gemm["step_ms"], "share_of_step_ncu": ncu_share,
+                            "share_note": "GEMM event time / duration of the same eagerly launched single-stream step; "
+                                          "ncu share from the committed launch list of this command", "step": step_rf}
     else:
         line["roofline"] = {"bound": "tensor", "kernel": "whole step", "achieved": ach, "peak": peaks["tflops_sustained"],
                             "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": None,

@@ -34,4 +34,5 @@ for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 if out_json and match:
     sel = [(n, t, b) for k, (n, t, b) in agg.items() if match in k]
     json.dump({"kernel": match, "launches": sum(x[0] for x in sel), "time_us": sum(x[1] for x in sel),
-               "dram_bytes_total": sum(x[2] for x in sel), "source": path}, open(out_json, "w"), indent=1)
+               "dram_bytes_total": sum(x[2] for x in sel), "all_kernels_time_us": tot,
+               "share_of_step": sum(x[1] for x in sel) / tot, "source": path}, open(out_json, "w"), indent=1)
