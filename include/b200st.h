@@ -2,7 +2,7 @@
  *
  * Drop-in boundary for bytedance/neurst (reference @ /root/reference).  The reference is pure Python; its
  * "FFI" for this path is the class registry (neurst/utils/registry.py:24-137) through which Trainer and the
- * models reach neurst/layers/** and neurst/criterions/**.  Each entry point below replaces the TF/PyTorch
+ * models reach the neurst/layers and neurst/criterions packages.  Each entry point below replaces the TF/PyTorch
  * library ops behind one reference function (file:line cited per function); INTEGRATION.md shows the
  * ctypes binding a maintainer adds.
  *

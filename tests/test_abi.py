@@ -61,3 +61,28 @@ def test_workspace_planning_and_errors():
     assert b"divisible" in lib.b200st_last_error()
     bad2 = make_config(L.MODEL_SPEECH, 36, 4, 64, 1, 1, 10, channels=8, precision="bf16")   # head dim 9 not % 8
     assert lib.b200st_create(C.byref(bad2), C.byref(h2)) != 0
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """include/b200st.h compiles as plain C (gcc, no CUDA headers) and every struct the ctypes binding mirrors has the
+    same size and field offsets as the C definition — the drop-in boundary cannot drift silently."""
+    import ctypes as C
+    import subprocess
+    pairs = [("b200st_operand", L.Operand), ("b200st_gemm_args", L.GemmArgs), ("b200st_config", L.Config),
+             ("b200st_buffers", L.Buffers), ("b200st_batch", L.Batch)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200st.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname + ".sizeof"]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
