@@ -1,12 +1,14 @@
 // Conv2d-subsampling front-end kernels (reference: neurst/layers/modalities/audio_modalities.py:84-109).
 //
-// conv1 (Cin small, K = 9*Cin) is bandwidth-bound: a direct CUDA-core convolution with the channel LayerNorm + ReLU
-// fused in — one warp per output position, channels across lanes (8 contiguous channels per lane => 16-byte
-// loads/stores along the feature axis), warp-shuffle statistics, filter taps in registers.
+// conv1 (Cin small, K = 9*Cin) is a direct CUDA-core convolution with the channel LayerNorm fused in — one warp per
+// output position, 8 contiguous channels per lane (16-byte loads/stores along the feature axis), warp-shuffle
+// statistics.  Production shape (C = 256, Cin = 1): filter taps in registers, and the training path stores the
+// NORMALISED activation xhat + 1/sigma ("normalised-save"): gamma/beta/ReLU are applied by the im2col in flight and the
+// backward reads xhat back, so it needs neither the convolution recompute nor the statistics.  Other shapes use the
+// generic kernels (filter in shared memory, post-ReLU activation stored, z1 recomputed in the backward).
 // conv2 is lowered to tcgen05 GEMMs through im2col (forward / wgrad) and a dcol GEMM (dgrad); the dgrad's col2im
-// gather is fused with the ReLU mask, the LayerNorm backward of conv1 (z1 recomputed from the fbank tile instead
-// of storing 164 M pre-activations) and the parameter-gradient partial sums.  conv1's filter gradient is then one
-// more split-K GEMM over the tiny im2col of the fbank (written by the same fused kernel).
+// gather is fused with the ReLU mask, the LayerNorm backward of conv1 and the parameter-gradient partial sums.
+// conv1's filter gradient is one more split-K GEMM over the tiny im2col of the fbank (written by the same kernel).
 #include "kernels.cuh"
 #include "pdl.cuh"
 
@@ -414,125 +416,6 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 2 : 1)) conv1_bwd_fused_kerne
 
 
 // ---------------------------------------------------------------------------------------------
-// Production fast path of the fused backward: C == 256, Cin == 1, LayerNorm on, 16-byte aligned rows.
-// Each warp walks a contiguous range of positions (incremental (b,t1,f1) decode), the 9 fbank taps are fetched by lanes
-// 0..8 and broadcast with shuffles, LN statistics use one (sum, sum-of-squares) reduction, no channel predicates.
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256, 2) conv1_bwd_fused_c256_kernel(
-    const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float eps, const T* __restrict__ y1, const T* __restrict__ dcol, T* __restrict__ dz1,
-    T* __restrict__ col1, int K1p, float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn,
-    int F, int T1, int F1, int T2, int F2) {
-  pdl_wait();
-  pdl_trigger();
-  constexpr int C = 256;
-  extern __shared__ float conv_smem[];   // filter [9][256] (slot-permuted) | bias [256] | partials [3][256]
-  float* sw = conv_smem; float* sb = conv_smem + 9 * C; float* sacc = sb + C;
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[(i / C) * C + slot_of_channel<true>(i % C)] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sb[slot_of_channel<true>(i)] = bias[i];
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  float greg[8], a_db[8], a_dg[8], a_dbe[8];
-  {
-    float t8[8];
-    ld8<float>(gamma + 8 * lane, t8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { greg[i] = t8[i]; a_db[i] = a_dg[i] = a_dbe[i] = 0.f; }
-  }
-  const int64_t npos = (int64_t)B * T1 * F1;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t per = (npos + nwarps - 1) / nwarps;
-  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int64_t pos = wid * per;
-  const int64_t pos_end = (pos + per < npos) ? pos + per : npos;
-  if (pos < pos_end) {
-    int f1 = (int)(pos % F1);
-    int t1 = (int)((pos / F1) % T1);
-    int b = (int)(pos / ((int64_t)F1 * T1));
-    const int tap_dt = lane / 3 - 1, tap_df = lane % 3 - 1;      // lanes 0..8 own one fbank tap each
-    for (; pos < pos_end; ++pos) {
-      // ---- issue all global loads of this position first ----
-      float xv = 0.f;
-      if (lane < 9) {
-        const int t = 2 * t1 + tap_dt, f = 2 * f1 + tap_df;
-        if (t >= 0 && t < Tn && f >= 0 && f < F) xv = __ldg(&src[((int64_t)b * Tn + t) * F + f]);
-      }
-      float yv[8];
-      ld8<T>(y1 + pos * C + 8 * lane, yv);
-      float d[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = 0.f;
-      // col2im: t1 even -> kh = 1 ; t1 odd -> kh in {0, 2} (same along f)
-      const int kh0 = (t1 & 1) ? 0 : 1, nkh = (t1 & 1) ? 2 : 1;
-      const int kw0 = (f1 & 1) ? 0 : 1, nkw = (f1 & 1) ? 2 : 1;
-      for (int a = 0; a < nkh; ++a) {
-        const int kh = kh0 + 2 * a;
-        const int t2 = (t1 + 1 - kh) >> 1;
-        if (t2 >= T2) continue;
-        for (int c2 = 0; c2 < nkw; ++c2) {
-          const int kw = kw0 + 2 * c2;
-          const int f2 = (f1 + 1 - kw) >> 1;
-          if (f2 >= F2) continue;
-          const int64_t row = ((int64_t)b * T2 + t2) * F2 + f2;
-          float t8[8];
-          ld8<T>(dcol + (row * 9 + kh * 3 + kw) * C + 8 * lane, t8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] += t8[i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (!(yv[i] > 0.f)) d[i] = 0.f;      // ReLU'
-      // ---- recompute z1 = conv(src) + b for this lane's 8 channels ----
-      float z[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) z[i] = sb[32 * i + lane];
-#pragma unroll
-      for (int tp = 0; tp < 9; ++tp) {
-        const float x = __shfl_sync(0xffffffffu, xv, tp);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = fmaf(x, sw[tp * C + 32 * i + lane], z[i]);
-      }
-      // ---- LayerNorm statistics (one pass) and backward ----
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s1 += z[i]; s2 = fmaf(z[i], z[i], s2); }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-      const float mean = s1 * (1.0f / C);
-      const float var = fmaxf(s2 * (1.0f / C) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
-      float c1 = 0.f, c2s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        z[i] = (z[i] - mean) * rstd;                 // xhat
-        const float g = d[i] * greg[i];
-        c1 += g; c2s = fmaf(g, z[i], c2s);
-        a_dg[i] = fmaf(d[i], z[i], a_dg[i]); a_dbe[i] += d[i];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { c1 += __shfl_xor_sync(0xffffffffu, c1, o); c2s += __shfl_xor_sync(0xffffffffu, c2s, o); }
-      c1 *= (1.0f / C); c2s *= (1.0f / C);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { d[i] = rstd * (d[i] * greg[i] - c1 - z[i] * c2s); a_db[i] += d[i]; }
-      st8<T>(dz1 + pos * C + 8 * lane, d);
-      if (lane < K1p) col1[pos * K1p + lane] = from_f32<T>(lane < 9 ? xv : 0.f);
-      if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = 8 * lane + i;
-    atomicAdd(&sacc[c], a_db[i]); atomicAdd(&sacc[C + c], a_dg[i]); atomicAdd(&sacc[2 * C + c], a_dbe[i]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&db[i], sacc[i]); atomicAdd(&dgamma[i], sacc[C + i]); atomicAdd(&dbeta[i], sacc[2 * C + i]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Backward from the saved normalised activations (C == 256, Cin == 1): col2im gather of dcol + ReLU' + LN' with xhat and
 // 1/sigma read back (no convolution recompute, no statistics), db/dgamma/dbeta partials, fbank im2col rows for dW1.
 // ---------------------------------------------------------------------------------------------
@@ -825,15 +708,6 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
   B200ST_CHECK(smem <= 48 * 1024, "conv1 filter does not fit the default shared memory");
   const bool vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dcol) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dz1) & 15) == 0);
-  if (vec && C == 256 && Cin == 1 && use_ln && K1p <= 32 && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0)) {
-    const int grid1 = pick_grid(npos, 8 * 16, 148 * 2);
-    const size_t smem1 = (size_t)(9 + 1 + 3) * 256 * sizeof(float);
-    DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_fused_c256_kernel<TT>, grid1, 256, smem1, s, src, w, b, gamma, beta, eps, (const TT*)y1,
-                                          (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2)));
-    ++g_kernel_launches;
-    B200ST_LAUNCH_CHECK();
-    return 0;
-  }
 #define BWD(VEC, CPL, CIN1)                                                                                             \
   DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_fused_kernel<TT, VEC, CPL, CIN1>, grid, 256, smem, s,                           \
       src, w, b, gamma, beta, eps, (const TT*)y1, (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, Cin, C, \
