@@ -1,12 +1,16 @@
 // Fused multi-head attention for sm_100a (head dim 64): S = QK^T and O = PV on tcgen05 with fp32 accumulators in
-// TMEM, operands staged by TMA, online softmax with one thread per query row (TMEM lane), additive key bias /
-// causal mask exactly as the reference (multi_head_attention.py:145-160: logits + bias, FLOAT_MIN = -1e9), Philox
-// dropout on the probabilities (:207-208).  The [B,H,Tq,Tk] score / probability tensors never touch HBM: forward
-// keeps only the per-row log-sum-exp; backward recomputes P from Q, K and the LSE (flash-attention style).
+// TMEM, operands staged by TMA, online softmax with one thread per (query row, half of a key block), additive key bias /
+// causal mask exactly as the reference (multi_head_attention.py:145-160: logits + bias, FLOAT_MIN = -1e9), dropout on
+// the probabilities (:207-208) from the precomputed keep-bit bitmap.  The [B,H,Tq,Tk] score / probability tensors never
+// touch HBM: forward keeps only the per-row log-sum-exp; backward recomputes P from Q, K and the LSE (flash-attention
+// style).
 //
-// forward : grid (q tiles of 128, H, B), 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax.
-// backward: grid (kv blocks of 128, H, B): K_j / V_j resident; loops over q tiles; dK_j, dV_j accumulate in TMEM,
-//           dQ tiles are reduced across kv blocks with fp32 vector RED into a scratch buffer.
+// forward : grid (q tiles of 128, H, B), 320 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax
+//           (2 per TMEM lane quadrant); two CTAs per SM.
+// backward: attn_bwd_prep_kernel (zero dQ, D = rowsum(dO * O)), then grid (kv blocks of 128, H, B), 320 threads: K_j / V_j
+//           resident; loops over q tiles; dK_j, dV_j accumulate in TMEM, dQ tiles are reduced across kv blocks with fp32
+//           vector RED into a scratch buffer (cast_rows_kernel -> bf16).
+// Measurement history and ncu findings: profiles/r01_attention_notes.md.
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "pdl.cuh"

@@ -3,9 +3,11 @@
 // Persistent, warp-specialised kernel (one CTA per SM, 320 threads):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM, 2 stages)
-//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global), 2 warps per TMEM lane quadrant
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> 128B-swizzled smem staging box -> TMA
+//                 store, or TMA reduce-add for split-K / accumulate), 2 warps per TMEM lane quadrant
 // Tile: 128 x BN x 64 (BN in {64,128,256}); operands may be K-major or MN-major (wgrad / PV products),
-// batched through 4-D tensor maps; optional split-K with fp32 RED accumulation.
+// batched through 4-D tensor maps; optional split-K.  Every launch is a programmatic dependent launch (pdl.cuh).
+// Measurements behind the design choices: profiles/r01_gemm_notes.md.
 //
 // Replaces the cuBLAS calls behind tf.einsum / Dense / Conv2D at the reference sites listed in
 // SURVEY.md §2.3 (K3,K4,K8,K9,K10,K11,K13,K15), e.g. neurst/layers/common_layers.py:270,276-288.
