@@ -86,3 +86,19 @@ def test_struct_layouts_match_the_c_header(tmp_path):
         assert int(got[cname + ".sizeof"]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No fallback: without the shared library the binding raises instead of degrading to any CPU / eager path, and a
+    Runtime refuses a non-CUDA device."""
+    import pytest
+    from neurst_b200 import lib as libmod
+    monkeypatch.setattr(libmod, "_lib", None)
+    monkeypatch.setattr(libmod, "_LIB_PATH", str(tmp_path / "libb200st_missing.so"))
+    with pytest.raises(libmod.B200STError):
+        libmod.load(build_if_missing=False)
+    monkeypatch.undo()
+    from neurst_b200.runtime import Runtime
+    cfg = make_config(L.MODEL_SPEECH, 16, 2, 32, 1, 1, 32, channels=8, feat=80, in_channels=1)
+    with pytest.raises(L.B200STError):
+        Runtime(cfg, device="cpu")
