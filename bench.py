@@ -53,6 +53,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.raw, self.windows, self.proc = index, False, [], [], None
+        import atexit
+        atexit.register(self.stop)          # never leave the nvidia-smi loop behind, whatever path the process exits by
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
