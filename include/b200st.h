@@ -20,6 +20,7 @@ extern "C" {
 
 #define B200ST_F32 0
 #define B200ST_BF16 1
+#define B200ST_F16 2   /* IEEE half: forward values of the mixed16 precision */
 
 const char* b200st_last_error(void);
 int b200st_version(void);

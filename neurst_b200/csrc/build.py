@@ -31,34 +31,69 @@ def _digest():
     return h.hexdigest()
 
 
+def is_current():
+    """True when the in-tree libb200st.so was built from exactly the sources (and flags) now in the tree."""
+    stamp = os.path.join(OBJ, "digest.txt")
+    return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == _digest()
+
+
 def build(force=False, verbose=False):
+    """Builds under an exclusive file lock (all ranks of a torchrun job call this at import: one compiles, the others
+    wait and find the library current) into temporary files that are os.replace()d into place, so no process can
+    dlopen a half-written library.  A stale library next to a failed build raises (never loads silently)."""
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
+    if not force and is_current():
+        return OUT
+    with open(os.path.join(OBJ, ".lock"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp = os.path.join(OBJ, "digest.txt")
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and is_current():       # another process built it while we waited for the lock
         return OUT
     if not os.path.exists(NVCC):
-        if os.path.exists(OUT):   # GPU box without a changed tree: use the shipped binary
-            return OUT
-        raise RuntimeError("nvcc not found and libb200st.so missing")
+        raise RuntimeError("libb200st.so is %s and nvcc (%s) is not available to rebuild it" %
+                           ("stale (source digest mismatch)" if os.path.exists(OUT) else "missing", NVCC))
     srcs = _sources()
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(HERE, src), "-o", obj]
+        # per-source incremental build: recompile only when this source (or any header / the flags) changed
+        h = hashlib.sha256(open(os.path.join(HERE, src), "rb").read())
+        for f in sorted(os.listdir(HERE)):
+            if f.endswith((".cuh", ".h")):
+                h.update(open(os.path.join(HERE, f), "rb").read())
+        h.update(open(os.path.join(HERE, "..", "..", "include", "b200st.h"), "rb").read())
+        h.update(" ".join(FLAGS).encode())
+        ostamp = obj + ".digest"
+        if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read() == h.hexdigest():
+            return obj
+        tmp = obj + ".tmp.%d" % os.getpid()
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(HERE, src), "-o", tmp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         if verbose:
             sys.stderr.write(r.stderr)
+        os.replace(tmp, obj)
+        open(ostamp, "w").write(h.hexdigest())
         return obj
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-cudart", "static"]
+    tmp_out = OUT + ".tmp.%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp_out] + objs + ["-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp_out, OUT)
     open(stamp, "w").write(dig)
     return OUT
 

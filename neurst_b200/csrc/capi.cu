@@ -22,7 +22,7 @@ using namespace b200st;
 extern "C" {
 
 const char* b200st_last_error(void) { return g_last_error.c_str(); }
-int b200st_version(void) { return 100; }
+int b200st_version(void) { return 200; }
 int64_t b200st_launch_count(void) { return g_kernel_launches + tc_launch_count(); }
 
 static GemmOperand to_operand(const b200st_operand& o) {

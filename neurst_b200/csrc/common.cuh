@@ -2,13 +2,18 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
 
 namespace b200st {
 
-enum DType : int { F32 = 0, BF16 = 1 };
+// F16 (IEEE half): forward values in the "mixed16" precision (11-bit significand: 8x finer than bf16, the reference's own
+// mixed_float16 compute type, neurst/training/training_utils.py:73-81); BF16: gradients (fp32 exponent range, no loss scaling).
+enum DType : int { F32 = 0, BF16 = 1, F16 = 2 };
+__host__ __device__ __forceinline__ bool is16(int dt) { return dt == BF16 || dt == F16; }
+__host__ __device__ __forceinline__ int dtype_size(int dt) { return dt == F32 ? 4 : 2; }
 
 // ---- error plumbing (thread-local last error string, C-ABI returns int) -----------------
 void set_last_error(const std::string& s);
@@ -46,19 +51,35 @@ cudaError_t& pdl_launch_error();
 template <typename T> struct DTypeOf;
 template <> struct DTypeOf<float> { static constexpr int value = F32; };
 template <> struct DTypeOf<__nv_bfloat16> { static constexpr int value = BF16; };
+template <> struct DTypeOf<__half> { static constexpr int value = F16; };
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// two fp32 -> one packed 16-bit pair (low half = a) in the 16-bit type `dt`
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, int dt) {
+  if (dt == F16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2_16(uint32_t u, int dt) {
+  if (dt == F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
 
 __device__ __forceinline__ float load_as_f32(const void* p, int dtype, int64_t idx) {
   return dtype == F32 ? reinterpret_cast<const float*>(p)[idx]
-                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+         : dtype == F16 ? __half2float(reinterpret_cast<const __half*>(p)[idx])
+                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
 }
 __device__ __forceinline__ void store_from_f32(void* p, int dtype, int64_t idx, float v) {
   if (dtype == F32) reinterpret_cast<float*>(p)[idx] = v;
+  else if (dtype == F16) reinterpret_cast<__half*>(p)[idx] = __float2half_rn(v);
   else reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16_rn(v);
 }
 

@@ -88,7 +88,7 @@ int gemm_simt_f32(const GemmArgs& g, cudaStream_t stream) {
 }
 
 int gemm(const GemmArgs& g, cudaStream_t stream) {
-  if (g.A.dtype == BF16 && g.B.dtype == BF16) return gemm_tc_bf16(g, stream);
+  if (is16(g.A.dtype) && is16(g.B.dtype)) return gemm_tc_bf16(g, stream);
   B200ST_CHECK(g.A.dtype == F32 && g.B.dtype == F32, "mixed-dtype GEMM operands");
   return gemm_simt_f32(g, stream);
 }

@@ -63,7 +63,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
   return t;
 }
 
-enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC = 2 };
+enum OutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC = 2, OUT_F16 = 3 };
+__host__ __device__ constexpr bool out_is16(int o) { return o == OUT_BF16 || o == OUT_F16; }
 
 // Cold path (ragged N, unaligned rows, on-the-fly Philox): compact, not unrolled, out of line — keeps the kernel's hot
 // code small enough for the instruction cache (the first version inlined every variant: 17 k SASS instructions).
@@ -79,7 +80,7 @@ __device__ __noinline__ void epilogue_chunk_general(const TcParams& p, const flo
     const int64_t idx = boff_c + (int64_t)m * p.ldc + n;
     if (p.atomic) atomicAdd(reinterpret_cast<float*>(p.C) + idx, v);
     else if (p.c_dtype == F32) reinterpret_cast<float*>(p.C)[idx] = ep.accumulate ? reinterpret_cast<float*>(p.C)[idx] + v : v;
-    else reinterpret_cast<__nv_bfloat16*>(p.C)[idx] = __float2bfloat16_rn(v);
+    else store_from_f32(p.C, p.c_dtype, idx, v);
   }
 }
 
@@ -116,17 +117,18 @@ __device__ __forceinline__ void epilogue_math(const TcParams& p, const uint32_t 
   }
   if (OUT == OUT_ATOMIC || !e.row_ok) return;
   if (e.mask) {
-    if (ep.mask_dtype == BF16) {
+    if (ep.mask_dtype != F32) {
+      // 16-bit mask source (bf16 or fp16): "> 0" <=> sign bit clear and magnitude bits non-zero, format-independent
       const uint4* mp = reinterpret_cast<const uint4*>(e.mask + co * 2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint4 pk = __ldg(mp + j);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          if (!(f.x > 0.f)) v[8 * j + 2 * i] = 0.f;
-          if (!(f.y > 0.f)) v[8 * j + 2 * i + 1] = 0.f;
+          const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+          if (!(lo != 0u && lo < 0x8000u)) v[8 * j + 2 * i] = 0.f;
+          if (!(hi != 0u && hi < 0x8000u)) v[8 * j + 2 * i + 1] = 0.f;
         }
       }
     } else {
@@ -162,15 +164,14 @@ template <int OUT>
 __device__ __forceinline__ void stage_chunk(uint32_t buf, int lane, int cb, const float (&v)[32]) {
   const uint32_t row = buf + (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7);
-  if (OUT == OUT_BF16) {
+  if (out_is16(OUT)) {
+    constexpr int dt = OUT == OUT_F16 ? F16 : BF16;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+      const uint32_t h0 = pack2_16(v[8 * j], v[8 * j + 1], dt), h1 = pack2_16(v[8 * j + 2], v[8 * j + 3], dt);
+      const uint32_t h2 = pack2_16(v[8 * j + 4], v[8 * j + 5], dt), h3 = pack2_16(v[8 * j + 6], v[8 * j + 7], dt);
       const uint32_t addr = row + ((((uint32_t)(cb * 4 + j)) ^ sw) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&h0)),
-                   "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
-                   : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
     }
   } else {
 #pragma unroll
@@ -325,11 +326,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         er.row_ok = m < p.M;
         er.bias = ep.bias ? ep.bias + n_base : nullptr;
         er.mask = (ep.mask_src && er.row_ok) ? reinterpret_cast<const char*>(ep.mask_src) +
-                                                   (size_t)(boff_mask + (int64_t)m * ep.mask_ld + n_base) * (ep.mask_dtype == BF16 ? 2 : 4)
+                                                   (size_t)(boff_mask + (int64_t)m * ep.mask_ld + n_base) * (ep.mask_dtype == F32 ? 4 : 2)
                                              : nullptr;
         er.res = (ep.residual && er.row_ok) ? ep.residual + boff_res + (int64_t)m * ep.res_ld + n_base : nullptr;
         er.bits = (ep.drop.p > 0.f && er.row_ok) ? ep.drop.bits + ((uint64_t)((bidx * p.M + m) * (int64_t)p.N + n_base) >> 3) : nullptr;
-        constexpr int kColsPerBox = (OUT == OUT_BF16) ? 64 : 32;
+        constexpr int kColsPerBox = out_is16(OUT) ? 64 : 32;
         // BN = 64 with bf16 output: one 64-column box per quadrant, written by the half-0 warp alone
         constexpr bool kSingle = (BN / 2 < kColsPerBox);
         constexpr int kBoxes = kSingle ? 1 : BN / 2 / kColsPerBox;
@@ -451,13 +452,14 @@ int make_operand_map(const GemmOperand& op, int rows, int K, int nb1, int nb2, i
   B200ST_CHECK(strides[0] % 16 == 0 && strides[1] % 16 == 0 && strides[2] % 16 == 0,
                "TMA operand strides must be multiples of 16 bytes (ld % 8 == 0 for bf16)");
   MapKey key{{(uint64_t)(uintptr_t)op.ptr, inner, outer, (uint64_t)nb1, (uint64_t)nb2, strides[0], strides[1], strides[2],
-              box[1], (uint64_t)op.mn_major}};
+              box[1], (uint64_t)op.mn_major | ((uint64_t)op.dtype << 8)}};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_map_cache.find(key);
     if (it != g_map_cache.end()) { *out = it->second; return 0; }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
+  CUresult r = fn(out, op.dtype == F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                  const_cast<void*>(op.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) B200ST_FAIL("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -483,13 +485,13 @@ int make_out_map(const void* C, int c_dtype, int N, int M, int nb1, int nb2, int
   if (strides[1] % 16 != 0) strides[1] = (strides[1] + 15) / 16 * 16;   // size-1 batch dims: any legal stride
   if (strides[2] % 16 != 0) strides[2] = (strides[2] + 15) / 16 * 16;
   MapKey key{{(uint64_t)(uintptr_t)C, (uint64_t)N, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2, strides[0], strides[1], strides[2],
-              0x1000u + es, 7u}};
+              0x1000u + es, 7u | ((uint64_t)c_dtype << 8)}};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_map_cache.find(key);
     if (it != g_map_cache.end()) { *out = it->second; return 0; }
   }
-  CUresult r = fn(out, c_dtype == F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(C), dims,
+  CUresult r = fn(out, c_dtype == F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : c_dtype == F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(C), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) B200ST_FAIL("cuTensorMapEncodeTiled (output) failed with CUresult " + std::to_string((int)r));
@@ -536,6 +538,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
                    cudaStream_t stream) {
   if (p.atomic) return launch_out<BN, A_MN, B_MN, OUT_ATOMIC>(ta, tb, tc, p, grid, smem, stream);
   if (p.c_dtype == F32) return launch_out<BN, A_MN, B_MN, OUT_F32>(ta, tb, tc, p, grid, smem, stream);
+  if (p.c_dtype == F16) return launch_out<BN, A_MN, B_MN, OUT_F16>(ta, tb, tc, p, grid, smem, stream);
   return launch_out<BN, A_MN, B_MN, OUT_BF16>(ta, tb, tc, p, grid, smem, stream);
 }
 
@@ -557,7 +560,7 @@ TcDebug& tc_debug() {
 int64_t tc_launch_count() { return g_launches; }
 
 int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
-  B200ST_CHECK(g.A.dtype == BF16 && g.B.dtype == BF16, "tcgen05 GEMM needs bf16 operands");
+  B200ST_CHECK(is16(g.A.dtype) && is16(g.B.dtype), "tcgen05 GEMM needs 16-bit (bf16 / fp16) operands");
   B200ST_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "empty GEMM");
   if (g_num_sms == 0) {
     int dev = 0;
@@ -640,7 +643,7 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   p.b_lbo = g.B.mn_major ? mn_lbo : k_lbo;  p.b_sbo = g.B.mn_major ? mn_sbo : k_sbo;
   p.a_kstep = g.A.mn_major ? 16u * 128u : 32u;
   p.b_kstep = g.B.mn_major ? 16u * 128u : 32u;
-  p.idesc = ptx::make_idesc_bf16(bn, g.A.mn_major, g.B.mn_major);
+  p.idesc = ptx::make_idesc_16(bn, g.A.mn_major, g.B.mn_major, g.A.dtype == BF16, g.B.dtype == BF16);
 
   p.C = g.C; p.c_dtype = g.c_dtype; p.ldc = g.ldc; p.c_sb1 = g.c_sb1; p.c_sb2 = g.c_sb2;
   p.epi = g.epi;
@@ -653,7 +656,7 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
                 (g.nb2 == 1 || (g.c_sb2 * esz_c) % 16 == 0) && g.N >= bn;
   if (g.epi.bias) tma_ok = tma_ok && al16(g.epi.bias);
   if (g.epi.mask_src) {
-    const uint64_t em = g.epi.mask_dtype == F32 ? 4 : 2;
+    const uint64_t em = g.epi.mask_dtype == F32 ? 4 : 2;   // bf16 and fp16 masks are both read as sign/magnitude words
     tma_ok = tma_ok && al16(g.epi.mask_src) && (g.epi.mask_ld * em) % 16 == 0 && (g.epi.mask_sb1 * em) % 16 == 0 &&
              (g.epi.mask_sb2 * em) % 16 == 0;
   }

@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libb200st.so")
 _lib = None
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+ABI_VERSION = 200    # must equal b200st_version(): bumped whenever a struct in include/b200st.h changes layout
 
 
 class B200STError(RuntimeError):
@@ -44,17 +45,19 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     if build_if_missing:
+        from neurst_b200.csrc import build as _build
         try:
-            from neurst_b200.csrc import build as _build
-            _build.build()
+            _build.build()          # no-op when the in-tree binary matches the source digest; locked + atomic otherwise
         except Exception as e:  # noqa
-            if not os.path.exists(_LIB_PATH):
-                raise B200STError("libb200st.so is missing and could not be built: %s" % e)
+            # a stale or missing library never loads silently: its struct layouts may no longer match the ctypes mirror
+            raise B200STError("libb200st.so is missing or stale and could not be (re)built: %s" % e)
     if not os.path.exists(_LIB_PATH):
         raise B200STError("libb200st.so not found at %s (run `python -m neurst_b200.csrc.build`)" % _LIB_PATH)
     lib = C.CDLL(_LIB_PATH)
     lib.b200st_last_error.restype = C.c_char_p
     lib.b200st_version.restype = C.c_int
+    if lib.b200st_version() != ABI_VERSION:
+        raise B200STError("libb200st.so ABI version %d != binding version %d" % (lib.b200st_version(), ABI_VERSION))
     lib.b200st_launch_count.restype = C.c_int64
     _declare(lib)
     _lib = lib
@@ -76,6 +79,8 @@ def _dt(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     raise B200STError("unsupported dtype %s" % t.dtype)
 
 

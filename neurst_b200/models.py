@@ -63,6 +63,10 @@ def _check_supported(args, speech):
     for side in ("encoder", "decoder"):
         if args.get(side + ".ffn_activation", "relu") != "relu" or args.get(side + ".attention_type", "dot_product") != "dot_product":
             raise NotImplementedError("only relu / dot_product are supported")
+    for k, dflt in (("attention_dropout_rate", 0.), ("ffn_dropout_rate", 0.), ("layer_postprocess_dropout_rate", 0.),
+                    ("layer_postprocess_epsilon", 1e-6)):
+        if args.get("encoder." + k, dflt) != args.get("decoder." + k, dflt):
+            raise NotImplementedError("libb200st uses one %s for both stacks (encoder.%s != decoder.%s)" % (k, k, k))
     if speech and (args.get("modality.source.kernel_size", 3) != 3 or args.get("modality.source.strides", 2) != 2):
         raise NotImplementedError("the conv front-end is 3x3 stride 2 (all reference presets)")
 

@@ -107,8 +107,11 @@ class Runtime:
             self.workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
         return self.workspace
 
-    def _buffers(self, nbytes, with_grads):
-        ws = self._workspace(nbytes)
+    def _buffers(self, nbytes, with_grads, ws=None):
+        """Buffers struct over the shared (grow-on-demand) workspace, or over a caller-owned tensor `ws` (CUDA-graph
+        steps bake the pointer into the captured graph, so each owns its workspace for its whole life)."""
+        if ws is None:
+            ws = self._workspace(nbytes)
         base = ws.data_ptr()
         aligned = (base + 255) // 256 * 256
         b = L.Buffers()
@@ -215,7 +218,9 @@ class GraphedTrainStep:
         need = int(rt.lib.b200st_workspace_bytes(rt.handle, B, T, Lq, 1))
         if need <= 0:
             raise L.B200STError("workspace planning failed: " + rt.lib.b200st_last_error().decode())
-        self.bufs = rt._buffers(need, True)
+        # the captured graph holds raw pointers into this tensor: owned here, never the runtime's growable workspace
+        self.workspace = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        self.bufs = rt._buffers(need, True, ws=self.workspace)
         bt = L.Batch()
         bt.src, bt.src_length = self.src.data_ptr(), self.src_length.data_ptr()
         bt.trg_input, bt.trg, bt.trg_length = self.trg_input.data_ptr(), self.trg.data_ptr(), self.trg_length.data_ptr()
@@ -258,4 +263,5 @@ class GraphedTrainStep:
         self.trg_length.copy_(batch["trg_length"], non_blocking=True)
         self.seed.fill_(int(seed))
         self.graph.replay()
-        return {"loss": self.loss, "nll_sum": self.nll_sum, "n_tokens": self.n_tokens}
+        # fresh tensors, as the eager path returns: the persistent outputs are overwritten by the next replay
+        return {"loss": self.loss.clone(), "nll_sum": self.nll_sum.clone(), "n_tokens": self.n_tokens.clone()}

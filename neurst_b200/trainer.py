@@ -81,14 +81,15 @@ class DataParallelTrainer:
         """fwd + bwd (+ all-reduce + Adam every `update_cycle` micro-batches).  Returns the device loss tensor."""
         b = dict(inputs)
         if seed is not None:
-            b["seed"] = seed
+            # independent dropout draws per replica (the reference's replicas seed their own RNG streams)
+            b["seed"] = int(seed) * self.world + self.rank
         if self.use_cuda_graph:
             from neurst_b200.runtime import GraphedTrainStep
             key = (b["src"].shape[0], b["src"].shape[1], b["trg_input"].shape[1])   # one graph per shape bucket
             if key not in self._graphs:
                 self._graphs[key] = GraphedTrainStep(self.rt, *key).capture()
             self._seed_ctr = getattr(self, "_seed_ctr", 0) + 1
-            out = self._graphs[key](b, b.get("seed", self._seed_ctr))
+            out = self._graphs[key](b, b.get("seed", self._seed_ctr * self.world + self.rank))
         else:
             out = self.model.forward_backward(b, is_training=True, loss_scale=1.0)
         self._micro += 1

@@ -189,3 +189,34 @@ def test_host_pipeline_matches_plain_loop(graph):
     for x, y in zip(plain, got):
         assert abs(x - y) < 2e-3 * max(1.0, abs(x)), (plain, got)
     assert pipe.h2d_bytes == sum(v.numel() * v.element_size() for v in hbs[0].values())
+
+
+def test_two_graph_buckets_keep_their_own_workspace():
+    """a second, larger shape bucket must not invalidate the pointers baked into an earlier graph.
+    Capture a small bucket, then a larger one and a bigger eager call (both grow the runtime's shared workspace), then
+    replay the small graph and compare with the eager result of the same batch / seed."""
+    from neurst_b200.runtime import GraphedTrainStep
+    cfg = dict(model="speech", d=64, heads=4, enc_layers=2, dec_layers=2, ffn=128, channels=64, feat=80, in_channels=1, vocab=96)
+    P = R.init_params(cfg, seed=7, random_bias=True)
+    rt = U.speech_runtime(cfg, "bf16", dropout=0.1, label_smoothing=0.1)
+    rt.load_parameters(P)
+    rt.ensure_grads().zero_()
+    small = U.to_cuda(U.synthetic_speech_batch(cfg, 2, 41, 7, seed=3))
+    big = U.to_cuda(U.synthetic_speech_batch(cfg, 6, 203, 19, seed=4))
+    g_small = GraphedTrainStep(rt, 2, 41, 7).capture()
+    g_big = GraphedTrainStep(rt, 6, 203, 19).capture()
+    eb = dict(big); eb.update(training=True, seed=5, want_logits=True)
+    rt.run(eb, backward=True)                      # eager call that reallocates the shared workspace
+    torch.cuda.empty_cache()
+    junk = torch.full((64 << 20,), 7, dtype=torch.uint8, device="cuda")   # whatever was freed gets reused
+    rt.grads.zero_()
+    es = dict(small); es.update(training=True, seed=77, want_logits=False)
+    loss_eager = float(rt.run(es, backward=True)["loss"]); g_eager = rt.grads.clone()
+    rt.grads.zero_()
+    loss_graph = float(g_small(small, 77)["loss"])
+    torch.cuda.synchronize()
+    assert abs(loss_graph - loss_eager) < 1e-6
+    assert U.rel_err(rt.grads, g_eager) < 1e-4
+    rt.grads.zero_()
+    float(g_big(big, 5)["loss"])
+    del junk
