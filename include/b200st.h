@@ -56,7 +56,11 @@ int b200st_gemm(const b200st_gemm_args* args, void* stream);
  * (neurst/models/transformer.py), 2 = TransformerEncoder stack only (layers/encoders/transformer_encoder.py:23-136),
  * 3 = TransformerDecoder stack only (layers/decoders/transformer_decoder.py:23-228), 4 = MultiHeadAttention /
  * MultiHeadSelfAttention (layers/attentions/multi_head_attention.py:21-290).
- * precision: B200ST_F32 = fp32 FMA kernels (parity mode, any shape); B200ST_BF16 = tcgen05 kernels. */
+ * precision: B200ST_F32 = fp32 FMA kernels (parity mode, any shape); B200ST_F16 / B200ST_BF16 = tcgen05 kernels with every
+ * 16-bit tensor (weights shadow, activations, activation gradients) in that type, fp32 accumulation, fp32 master weights,
+ * fp32 parameter gradients.  B200ST_F16 is the reference's own mixed precision (mixed_float16 + dynamic loss scaling,
+ * neurst/training/training_utils.py:73-81,413-416): 11-bit significands, needs loss scaling (b200st_batch.loss_scale_dev +
+ * b200st_optimizer_step); B200ST_BF16 needs none but carries 8-bit significands. */
 typedef struct b200st_model* b200st_handle;
 typedef struct {
   int32_t model_type;
@@ -82,7 +86,7 @@ int b200st_param_info(b200st_handle h, int32_t i, char* name, int32_t name_cap, 
 
 typedef struct {
   const float* params;      /* fp32 master arena */
-  const void* shadow;       /* bf16 copy of the arena (precision bf16 only; b200st_refresh_shadow / b200st_adam_step) */
+  const void* shadow;       /* 16-bit copy of the arena in the handle's precision (b200st_refresh_shadow / b200st_optimizer_step) */
   float* grads;             /* fp32, same layout; gradients are ACCUMULATED into it */
   void* workspace; uint64_t workspace_bytes;   /* >= b200st_workspace_bytes(...) , 256-byte aligned */
 } b200st_buffers;
@@ -101,6 +105,8 @@ typedef struct {
   uint64_t seed;                /* dropout seed of this step */
   const uint64_t* seed_dev;     /* optional device-resident seed (read at kernel run time: CUDA-graph replay) */
   float loss_scale;             /* multiplies the loss gradient (0 => 1) */
+  const float* loss_scale_dev;  /* optional device word, multiplied in too: the dynamic loss scale (element 0 of the
+                                 * b200st_optimizer_step state), read at kernel run time so CUDA-graph replays follow it */
   float* logits;                /* out, optional: fp32 [B,L,V] */
   float* loss;                  /* out, optional: [1] = sum(nll)/sum(tokens) (label_smoothed_cross_entropy.py:46-53) */
   float* nll_sum;               /* out, optional: [B] */
@@ -114,9 +120,31 @@ int b200st_forward(b200st_handle h, const b200st_buffers* buf, const b200st_batc
 /* forward + label-smoothed CE + full backward (GradAccumKerasModel.train_step, gradaccum_keras_model.py:190-245) */
 int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream);
 
-/* bf16 shadow of the parameter arena (tcgen05 operands) */
-int b200st_refresh_shadow(const float* params, void* shadow, int64_t numel, void* stream);
-/* Keras Adam, epsilon-hat form (neurst/optimizers/__init__.py:21; hparams speech_transformer.py:265-270):
+/* 16-bit shadow of the parameter arena (tcgen05 operands); shadow_dtype = B200ST_BF16 or B200ST_F16 */
+int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtype, int64_t numel, void* stream);
+
+/* Optimizer step of GradAccumKerasModel.train_step (neurst/training/gradaccum_keras_model.py:222-240): unscale ->
+ * tf.clip_by_value / tf.clip_by_norm PER GRADIENT TENSOR -> Keras Adam (epsilon-hat form), with the 16-bit shadow refresh and
+ * gradient zeroing in the same pass.  loss_scale_state != NULL enables the reference's dynamic loss scale
+ * (neurst/training/revised_dynamic_loss_scale.py:60-107): device float[8] = {scale, finite steps in a row, last step skipped,
+ * skipped steps, applied steps, global gradient norm, 1/scale latch, reserved}; a step whose gradients are not all finite
+ * is skipped (parameters untouched, gradients zeroed) and halves the scale; `growth_steps` finite steps double it.
+ * h may be NULL (whole arena = one tensor). tensor_sumsq: device float[param_count + 1] scratch (clip_norm / loss scale). */
+typedef struct {
+  float* params; float* grads; float* m; float* v;
+  void* shadow; int32_t shadow_dtype;
+  int64_t numel;
+  float lr, beta1, beta2, eps;
+  int64_t step_t;               /* Adam's t (from 1) when loss_scale_state is NULL; else t = applied steps on the device */
+  float grad_scale;             /* 1 / (replicas * update_cycle) */
+  int32_t zero_grad;
+  float clip_value, clip_norm;  /* <= 0: off */
+  float* tensor_sumsq;
+  float* loss_scale_state;
+  float growth_steps, multiplier;   /* 0 => 2000, 2 */
+} b200st_optim_args;
+int b200st_optimizer_step(b200st_handle h, const b200st_optim_args* a, void* stream);
+/* legacy form: plain Keras Adam with a bf16 shadow, epsilon-hat form (neurst/optimizers/__init__.py:21; hparams speech_transformer.py:265-270):
  * g' = g*grad_scale; m,v update; p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps); optional bf16 shadow refresh + g=0 */
 int b200st_adam_step(float* params, float* grads, float* m, float* v, void* shadow, int64_t numel, float lr, float beta1,
                      float beta2, float eps, int64_t step_t, float grad_scale, int32_t zero_grad, void* stream);

@@ -18,8 +18,8 @@
 
 namespace b200st {
 
-int make_tma_map_bf16(const void* ptr, uint64_t inner, uint64_t rows, int nb1, int nb2, int64_t ld, int64_t sb1, int64_t sb2,
-                      uint32_t box_rows, CUtensorMap* out);
+int make_tma_map_16(const void* ptr, int dtype, uint64_t inner, uint64_t rows, int nb1, int nb2, int64_t ld, int64_t sb1, int64_t sb2,
+                    uint32_t box_rows, CUtensorMap* out);
 
 namespace {
 
@@ -35,14 +35,14 @@ struct AttnParams {
   const float* bias;           // [B, Tk] additive or null
   int causal;
   DropoutSpec drop;
-  __nv_bfloat16* ctx; int64_t ctx_ld;     // [B*Tq, H*64]
+  uint16_t* ctx; int64_t ctx_ld;          // [B*Tq, H*64], 16-bit type DT (bf16 or fp16)
   float* lse;                  // [B, H, Tq]  (natural log)
   // backward only
-  const __nv_bfloat16* dctx; int64_t dctx_ld;
+  const uint16_t* dctx; int64_t dctx_ld;
   float* dq_acc; int64_t dq_ld;           // fp32 [B*Tq, H*64] (zeroed by attn_bwd_prep_kernel)
   const float* dvec;                      // [B, H, Tq] rowsum(dO * O) (attn_bwd_prep_kernel)
-  __nv_bfloat16* dk; int64_t dk_ld;       // [B*Tk, ...] view base already offset to the K columns; + h*64
-  __nv_bfloat16* dv; int64_t dv_ld;
+  uint16_t* dk; int64_t dk_ld;            // [B*Tk, ...] view base already offset to the K columns; + h*64
+  uint16_t* dv; int64_t dv_ld;
 };
 
 __device__ __forceinline__ float logit(const AttnParams& p, float s, const float* bias_row, int k, int q) {
@@ -62,10 +62,9 @@ __device__ __forceinline__ uint32_t swz_off(int row, int col) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+// every kernel below is templated on DT, the 16-bit operand type (BF16 or F16): it only selects the MMA operand format
+// bits and the fp32 <-> 16-bit conversions
+#define pack_bf16(a, b) pack2_16((a), (b), DT)
 
 // ==============================================================================================================
 // forward: 320 threads = TMA warp + MMA warp + 8 softmax warps (2 per TMEM lane quadrant, each owning 64 of the 128
@@ -110,7 +109,7 @@ __device__ __forceinline__ void load_keep64(const DropoutSpec& d, bool row_ok, i
   }
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, int DT>
 __global__ void __launch_bounds__(320, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -171,8 +170,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = ptx::make_idesc_bf16(BKV, 0, 0);    // S[128 x 128] = Q K^T, both K-major
-      const uint32_t idesc_o = ptx::make_idesc_bf16(DH, 0, 1);     // O[128 x 64] += P V, V as MN-major B
+      constexpr int kBf = DT == BF16 ? 1 : 0;
+      const uint32_t idesc_s = ptx::make_idesc_16(BKV, 0, 0, kBf, kBf);    // S[128 x 128] = Q K^T, both K-major
+      const uint32_t idesc_o = ptx::make_idesc_16(DH, 0, 1, kBf, kBf);     // O[128 x 64] += P V, V as MN-major B
       ptx::mbar_wait(q_full, 0);
       for (int j = 0; j < nblk; ++j) {
         const uint32_t ph = (uint32_t)j & 1u;
@@ -302,7 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_wait(o_ready, (uint32_t)(nblk - 1) & 1u);
     ptx::tc_fence_after();
     const float inv_l = ((p.drop.p > 0.f) ? p.drop.scale : 1.0f) / l;
-    __nv_bfloat16* dst = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH + half * 32;
+    uint16_t* dst = p.ctx + ((int64_t)b * p.Tq + q) * p.ctx_ld + h * DH + half * 32;
     {
       uint32_t ro[32];
       __syncwarp();
@@ -335,7 +335,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, int DT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnParams p) {
@@ -396,9 +396,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = ptx::make_idesc_bf16(BKV, 0, 0);    // [128q x 128k], A,B K-major
-      const uint32_t idesc_kv = ptx::make_idesc_bf16(DH, 1, 1);    // dV/dK [128k x 64] = X^T Y : A, B MN-major
-      const uint32_t idesc_q = ptx::make_idesc_bf16(DH, 0, 1);     // dQ [128q x 64] = dS K : A K-major, B MN-major
+      constexpr int kBf = DT == BF16 ? 1 : 0;
+      const uint32_t idesc_s = ptx::make_idesc_16(BKV, 0, 0, kBf, kBf);    // [128q x 128k], A,B K-major
+      const uint32_t idesc_kv = ptx::make_idesc_16(DH, 1, 1, kBf, kBf);    // dV/dK [128k x 64] = X^T Y : A, B MN-major
+      const uint32_t idesc_q = ptx::make_idesc_16(DH, 0, 1, kBf, kBf);     // dQ [128q x 64] = dS K : A K-major, B MN-major
       ptx::mbar_wait(kv_full, 0);
       for (int i = 0; i < nq; ++i) {
         const int st = i & 1;
@@ -540,8 +541,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them); 32 columns per half ----
     const int kk = jb * BKV + row;
-    __nv_bfloat16* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH + half * 32;
-    __nv_bfloat16* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH + half * 32;
+    uint16_t* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH + half * 32;
+    uint16_t* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH + half * 32;
     {
       uint32_t rv[32], rk[32];
       __syncwarp();
@@ -575,7 +576,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 constexpr size_t kBwdSmem = 1024 + (size_t)(2 + 2 + 2 + 2 + 2) * kTile16K + 128 + 512 + 64;
 
 // One warp per (b, q) row: zero the fp32 dQ accumulator row and compute D[b,h,q] = sum_c dO[b,q,h,c] * O[b,q,h,c].
-__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_t o_ld, const __nv_bfloat16* __restrict__ dout,
+template <int DT>
+__global__ void attn_bwd_prep_kernel(const uint16_t* __restrict__ o, int64_t o_ld, const uint16_t* __restrict__ dout,
                                      int64_t do_ld, float* __restrict__ dq_acc, float* __restrict__ dvec, int B, int H, int Tq) {
   pdl_wait();
   pdl_trigger();
@@ -589,11 +591,10 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_
       float part = 0.f;
       if (c < chunks) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + r * o_ld + 8 * c)), d = __ldg(reinterpret_cast<const uint4*>(dout + r * do_ld + 8 * c));
-        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-        const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float2 x = __bfloat1622float2(ah[t]), y = __bfloat1622float2(dh[t]);
+          const float2 x = unpack2_16(aw[t], DT), y = unpack2_16(dw[t], DT);
           part = fmaf(x.x, y.x, fmaf(x.y, y.y, part));
         }
         float4* z = reinterpret_cast<float4*>(dq_acc + r * (int64_t)H * DH + 8 * c);
@@ -608,7 +609,8 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_
 }
 
 // dst(bf16)[r, 0..cols) = src(fp32)[r, 0..cols)   (dq scratch -> the q columns of the fused dqkv buffer)
-__global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst,
+template <int DT>
+__global__ void cast_rows_kernel(const float* __restrict__ src, int64_t ld_src, uint16_t* __restrict__ dst, int64_t ld_dst,
                                  int64_t rows, int cols) {
   pdl_wait();
   pdl_trigger();
@@ -628,32 +630,34 @@ constexpr size_t kFwdSmemFixed = 1024 + (size_t)(1 + 2 + 1 + 2) * kTile16K + 307
 }  // namespace
 
 // q/k/v: bf16 views [B*T, ld] with head h at columns [h*64, h*64+64)
-int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
+int attention_fwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
                         int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
                         cudaStream_t s) {
   B200ST_CHECK(Tq > 0 && Tk > 0 && B > 0 && H > 0, "empty attention");
   B200ST_CHECK(B <= 65535 && H <= 65535, "attention grid too large");
+  B200ST_CHECK(is16(dt), "fused attention needs a 16-bit operand type");
   CUtensorMap tq, tk, tv;
-  B200ST_TRY(make_tma_map_bf16(q, DH, Tq, H, B, q_ld, DH, (int64_t)Tq * q_ld, BQ, &tq));
-  B200ST_TRY(make_tma_map_bf16(k, DH, Tk, H, B, k_ld, DH, (int64_t)Tk * k_ld, BKV, &tk));
-  B200ST_TRY(make_tma_map_bf16(v, DH, Tk, H, B, v_ld, DH, (int64_t)Tk * v_ld, BKV, &tv));
+  B200ST_TRY(make_tma_map_16(q, dt, DH, Tq, H, B, q_ld, DH, (int64_t)Tq * q_ld, BQ, &tq));
+  B200ST_TRY(make_tma_map_16(k, dt, DH, Tk, H, B, k_ld, DH, (int64_t)Tk * k_ld, BKV, &tk));
+  B200ST_TRY(make_tma_map_16(v, dt, DH, Tk, H, B, v_ld, DH, (int64_t)Tk * v_ld, BKV, &tv));
   AttnParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.Tkp = (Tk + 7) / 8 * 8;
   p.alpha = 0.125f;                     // 64^-0.5 (multi_head_attention.py:203)
   p.bias = bias; p.causal = causal; p.drop = drop;
-  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx); p.ctx_ld = ctx_ld; p.lse = lse;
+  p.ctx = reinterpret_cast<uint16_t*>(ctx); p.ctx_ld = ctx_ld; p.lse = lse;
   B200ST_CHECK((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && ctx_ld % 8 == 0, "ctx must be 16-byte aligned");
   const size_t smem = kFwdSmemFixed + (size_t)((Tk + BKV - 1) / BKV) * 512;
   B200ST_CHECK(smem <= 227 * 1024, "fused attention: Tk too large for the shared-memory bias table");
-  static size_t attr[2] = {0, 0};
-  if (smem > attr[causal ? 1 : 0]) {
-    if (causal) B200ST_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else B200ST_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[causal ? 1 : 0] = smem;
+  auto kern = causal ? (dt == F16 ? attn_fwd_kernel<true, F16> : attn_fwd_kernel<true, BF16>)
+                     : (dt == F16 ? attn_fwd_kernel<false, F16> : attn_fwd_kernel<false, BF16>);
+  static size_t attr[4] = {0, 0, 0, 0};
+  const int ai = (causal ? 1 : 0) + (dt == F16 ? 2 : 0);
+  if (smem > attr[ai]) {
+    B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[ai] = smem;
   }
   dim3 grid((Tq + BQ - 1) / BQ, H, B);
-  if (causal) launch_pdl(attn_fwd_kernel<true>, grid, 320, smem, s, tq, tk, tv, p);
-  else launch_pdl(attn_fwd_kernel<false>, grid, 320, smem, s, tq, tk, tv, p);
+  launch_pdl(kern, grid, 320, smem, s, tq, tk, tv, p);
   tc_count_launch();
   B200ST_LAUNCH_CHECK();
   return 0;
@@ -661,32 +665,35 @@ int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
 
 
 // dq_scratch: fp32 [B*Tq, H*64] (overwritten).  dq/dk/dv: bf16 views like q/k/v.  lse / ctx from the forward pass.
-int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
+int attention_bwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
                         int64_t ctx_ld, const void* dctx, int64_t dctx_ld, const float* lse, int B, int H, int Tq, int Tk,
                         const float* bias, int causal, DropoutSpec drop, float* dq_scratch, void* dq, int64_t dq_ld, void* dk,
                         int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s) {
   B200ST_CHECK(Tq > 0 && Tk > 0 && B > 0 && H > 0 && B <= 65535 && H <= 65535, "bad attention shape");
+  B200ST_CHECK(is16(dt), "fused attention needs a 16-bit operand type");
   CUtensorMap tq, tk, tv, tdo;
-  B200ST_TRY(make_tma_map_bf16(q, DH, Tq, H, B, q_ld, DH, (int64_t)Tq * q_ld, BQ, &tq));
-  B200ST_TRY(make_tma_map_bf16(k, DH, Tk, H, B, k_ld, DH, (int64_t)Tk * k_ld, BKV, &tk));
-  B200ST_TRY(make_tma_map_bf16(v, DH, Tk, H, B, v_ld, DH, (int64_t)Tk * v_ld, BKV, &tv));
-  B200ST_TRY(make_tma_map_bf16(dctx, DH, Tq, H, B, dctx_ld, DH, (int64_t)Tq * dctx_ld, BQ, &tdo));
+  B200ST_TRY(make_tma_map_16(q, dt, DH, Tq, H, B, q_ld, DH, (int64_t)Tq * q_ld, BQ, &tq));
+  B200ST_TRY(make_tma_map_16(k, dt, DH, Tk, H, B, k_ld, DH, (int64_t)Tk * k_ld, BKV, &tk));
+  B200ST_TRY(make_tma_map_16(v, dt, DH, Tk, H, B, v_ld, DH, (int64_t)Tk * v_ld, BKV, &tv));
+  B200ST_TRY(make_tma_map_16(dctx, dt, DH, Tq, H, B, dctx_ld, DH, (int64_t)Tq * dctx_ld, BQ, &tdo));
   AttnParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.Tkp = (Tk + 7) / 8 * 8;
   p.alpha = 0.125f;
   p.bias = bias; p.causal = causal; p.drop = drop;
-  p.ctx = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ctx)); p.ctx_ld = ctx_ld;
+  p.ctx = reinterpret_cast<uint16_t*>(const_cast<void*>(ctx)); p.ctx_ld = ctx_ld;
   p.lse = const_cast<float*>(lse);
-  p.dctx = reinterpret_cast<const __nv_bfloat16*>(dctx); p.dctx_ld = dctx_ld;
+  p.dctx = reinterpret_cast<const uint16_t*>(dctx); p.dctx_ld = dctx_ld;
   p.dq_acc = dq_scratch; p.dq_ld = (int64_t)H * DH;
-  p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_ld = dk_ld;
-  p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_ld = dv_ld;
+  p.dk = reinterpret_cast<uint16_t*>(dk); p.dk_ld = dk_ld;
+  p.dv = reinterpret_cast<uint16_t*>(dv); p.dv_ld = dv_ld;
   B200ST_CHECK(((reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(dq) |
                  reinterpret_cast<uintptr_t>(dq_scratch)) & 15) == 0, "attention gradient buffers must be 16-byte aligned");
   static bool attr = false;
   if (!attr) {
-    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    B200ST_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     attr = true;
   }
   const int64_t rows = (int64_t)B * Tq;
@@ -697,19 +704,21 @@ int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld
   {
     int64_t gp = (rows + 7) / 8;
     if (gp > 148 * 8) gp = 148 * 8;
-    launch_pdl(attn_bwd_prep_kernel, (int)gp, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(ctx), ctx_ld,
-               reinterpret_cast<const __nv_bfloat16*>(dctx), dctx_ld, dq_scratch, dvec, B, H, Tq);
+    launch_pdl(dt == F16 ? attn_bwd_prep_kernel<F16> : attn_bwd_prep_kernel<BF16>, (int)gp, 256, 0, s,
+               reinterpret_cast<const uint16_t*>(ctx), ctx_ld, reinterpret_cast<const uint16_t*>(dctx), dctx_ld, dq_scratch, dvec, B, H, Tq);
     g_kernel_launches += 1;
     B200ST_LAUNCH_CHECK();
   }
   dim3 grid((Tk + BKV - 1) / BKV, H, B);
-  if (causal) launch_pdl(attn_bwd_kernel<true>, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
-  else launch_pdl(attn_bwd_kernel<false>, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
+  auto kern = causal ? (dt == F16 ? attn_bwd_kernel<true, F16> : attn_bwd_kernel<true, BF16>)
+                     : (dt == F16 ? attn_bwd_kernel<false, F16> : attn_bwd_kernel<false, BF16>);
+  launch_pdl(kern, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
   B200ST_LAUNCH_CHECK();
   const int64_t n8 = rows * (H * DH / 8);
   int64_t g = (n8 + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  launch_pdl(cast_rows_kernel, (int)g, 256, 0, s, dq_scratch, (int64_t)H * DH, reinterpret_cast<__nv_bfloat16*>(dq), dq_ld, rows, H * DH);
+  launch_pdl(dt == F16 ? cast_rows_kernel<F16> : cast_rows_kernel<BF16>, (int)g, 256, 0, s, dq_scratch, (int64_t)H * DH,
+             reinterpret_cast<uint16_t*>(dq), dq_ld, rows, H * DH);
   tc_count_launch();
   g_kernel_launches += 1;
   B200ST_LAUNCH_CHECK();

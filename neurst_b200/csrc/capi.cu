@@ -137,7 +137,7 @@ int b200st_param_info(b200st_handle h, int32_t i, char* name, int32_t name_cap, 
 static Buffers to_buffers(const b200st_buffers* b) {
   Buffers r{};
   if (b) {
-    r.params = b->params; r.shadow = reinterpret_cast<const __nv_bfloat16*>(b->shadow); r.grads = b->grads;
+    r.params = b->params; r.shadow = b->shadow; r.grads = b->grads;
     r.workspace = b->workspace; r.workspace_bytes = (size_t)b->workspace_bytes;
   }
   return r;
@@ -146,7 +146,7 @@ static Batch to_batch(const b200st_batch* b) {
   Batch r{};
   r.src = b->src; r.src_ids = b->src_ids; r.src_length = b->src_length; r.src_padding = b->src_padding;
   r.trg_input = b->trg_input; r.trg = b->trg; r.trg_length = b->trg_length;
-  r.B = b->B; r.T = b->T; r.L = b->L; r.training = b->training; r.seed = b->seed; r.seed_dev = b->seed_dev; r.loss_scale = b->loss_scale;
+  r.B = b->B; r.T = b->T; r.L = b->L; r.training = b->training; r.seed = b->seed; r.seed_dev = b->seed_dev; r.loss_scale = b->loss_scale; r.loss_scale_dev = b->loss_scale_dev;
   r.logits = b->logits; r.loss = b->loss; r.nll_sum = b->nll_sum; r.n_tokens = b->n_tokens; r.enc_out = b->enc_out;
   return r;
 }
@@ -165,17 +165,44 @@ int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b2
   if (batch->B <= 0 || batch->T <= 0 || batch->L <= 0) B200ST_FAIL("empty batch");
   return model_forward(h->m, to_buffers(buf), to_batch(batch), true, reinterpret_cast<cudaStream_t>(stream));
 }
-int b200st_refresh_shadow(const float* params, void* shadow, int64_t numel, void* stream) {
+int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtype, int64_t numel, void* stream) {
   if (!params || !shadow) B200ST_FAIL("null argument");
-  return cast_f32_to_bf16(params, reinterpret_cast<__nv_bfloat16*>(shadow), numel, reinterpret_cast<cudaStream_t>(stream));
+  return cast_f32_to_16(params, shadow, shadow_dtype, numel, reinterpret_cast<cudaStream_t>(stream));
+}
+static void fill_tensor_table(const Model& m, TensorTable& tt) {
+  tt.n = 0;
+  if (m.params.size() > 512) return;
+  for (const ParamInfo& p : m.params) tt.off8[tt.n++] = (uint32_t)(p.offset >> 3);
+  tt.off8[tt.n] = (uint32_t)(m.arena_numel >> 3);
+}
+int b200st_optimizer_step(b200st_handle h, const b200st_optim_args* a, void* stream) {
+  if (!a || !a->params || !a->grads || !a->m || !a->v) B200ST_FAIL("bad optimizer arguments");
+  if (!a->loss_scale_state && a->step_t < 1) B200ST_FAIL("step_t counts from 1");
+  OptimArgs o{};
+  o.p = a->params; o.g = a->grads; o.m = a->m; o.v = a->v;
+  o.shadow = a->shadow; o.shadow_dtype = a->shadow_dtype;
+  o.n = a->numel;
+  o.lr = a->lr; o.beta1 = a->beta1; o.beta2 = a->beta2; o.eps = a->eps; o.step_t = a->step_t;
+  o.grad_scale = a->grad_scale; o.zero_grad = a->zero_grad;
+  o.clip_value = a->clip_value; o.clip_norm = a->clip_norm;
+  o.tensor_sumsq = a->tensor_sumsq; o.ctl = a->loss_scale_state;
+  o.growth_steps = a->growth_steps; o.multiplier = a->multiplier;
+  TensorTable tt{};
+  if (h) {
+    if (a->numel != h->m.arena_numel) B200ST_FAIL("numel does not match the handle's parameter arena");
+    fill_tensor_table(h->m, tt);
+  } else if (a->clip_norm > 0.f || a->loss_scale_state) {
+    // no handle: the whole arena is one tensor
+    tt.n = 1; tt.off8[0] = 0; tt.off8[1] = (uint32_t)((a->numel + 7) >> 3);
+  }
+  return optimizer_step(o, tt, reinterpret_cast<cudaStream_t>(stream));
 }
 int b200st_adam_step(float* params, float* grads, float* m, float* v, void* shadow, int64_t numel, float lr, float beta1,
                      float beta2, float eps, int64_t step_t, float grad_scale, int32_t zero_grad, void* stream) {
-  if (!params || !grads || !m || !v || step_t < 1) B200ST_FAIL("bad adam arguments");
-  const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step_t)) /
-                      (1.0 - std::pow((double)beta1, (double)step_t));
-  return adam_step(params, grads, m, v, reinterpret_cast<__nv_bfloat16*>(shadow), numel, (float)lr_t, beta1, beta2, eps,
-                   grad_scale, zero_grad, reinterpret_cast<cudaStream_t>(stream));
+  b200st_optim_args a{};
+  a.params = params; a.grads = grads; a.m = m; a.v = v; a.shadow = shadow; a.shadow_dtype = B200ST_BF16; a.numel = numel;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step_t = step_t; a.grad_scale = grad_scale; a.zero_grad = zero_grad;
+  return b200st_optimizer_step(nullptr, &a, stream);
 }
 int b200st_encoder_forward(b200st_handle h, const b200st_buffers* buf, const float* x, const float* padding, int32_t B,
                            int32_t T, float* out, int32_t training, uint64_t seed, void* stream, uint64_t* need_bytes) {
@@ -210,7 +237,7 @@ int b200st_lsce(const float* logits, const int64_t* trg, const int64_t* trg_leng
                 float loss_scale, void* stream) {
   if (!logits || !trg || !trg_length || !nll_sum || !n_tokens || !loss) B200ST_FAIL("null argument");
   return lsce_fwd_bwd(logits, trg, trg_length, B, L, V, label_smoothing, nll_sum, n_tokens, loss, dlogits, dlogits_dtype,
-                      loss_scale > 0.f ? loss_scale : 1.f, reinterpret_cast<cudaStream_t>(stream));
+                      loss_scale > 0.f ? loss_scale : 1.f, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 int b200st_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps, void* y,
                          int32_t y_dtype, float* mean, float* rstd, int64_t rows, int32_t cols, int32_t relu, void* stream) {

@@ -18,6 +18,7 @@ namespace b200st {
   do {                                                               \
     if ((dt) == F32) { using T = float; __VA_ARGS__; }               \
     else if ((dt) == BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((dt) == F16) { using T = __half; __VA_ARGS__; }         \
     else B200ST_FAIL("bad dtype");                                   \
   } while (0)
 
@@ -28,38 +29,41 @@ template <> __device__ __forceinline__ void ld8<float>(const float* src, float (
   const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[8]) {
-  const uint4 pk = __ldg(reinterpret_cast<const uint4*>(src));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+template <int DT> __device__ __forceinline__ void unpack8_16(const uint4& pk, float (&v)[8]) {
+  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  for (int i = 0; i < 4; ++i) { const float2 f = unpack2_16(w[i], DT); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[8]) {
+  unpack8_16<BF16>(__ldg(reinterpret_cast<const uint4*>(src)), v);
+}
+template <> __device__ __forceinline__ void ld8<__half>(const __half* src, float (&v)[8]) {
+  unpack8_16<F16>(__ldg(reinterpret_cast<const uint4*>(src)), v);
 }
 template <typename T> __device__ __forceinline__ void st8(T* dst, const float (&v)[8]);
 template <> __device__ __forceinline__ void st8<float>(float* dst, const float (&v)[8]) {
   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[8]) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+template <int DT> __device__ __forceinline__ void st8_16(void* dst, const float (&v)[8]) {
   uint4 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-  pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  pk.x = pack2_16(v[0], v[1], DT); pk.y = pack2_16(v[2], v[3], DT);
+  pk.z = pack2_16(v[4], v[5], DT); pk.w = pack2_16(v[6], v[7], DT);
   *reinterpret_cast<uint4*>(dst) = pk;
 }
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[8]) { st8_16<BF16>(dst, v); }
+template <> __device__ __forceinline__ void st8<__half>(__half* dst, const float (&v)[8]) { st8_16<F16>(dst, v); }
 
 // 8 consecutive elements held in raw form (prefetch registers: 16 B for bf16, 32 B for fp32)
 template <typename T> struct Vec8;
-template <> struct Vec8<__nv_bfloat16> {
+template <typename T16, int DT> struct Vec8_16 {
   uint4 r;
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void load(const T16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
   __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
-  __device__ __forceinline__ void get(float (&v)[8]) const {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-  }
+  __device__ __forceinline__ void get(float (&v)[8]) const { unpack8_16<DT>(r, v); }
 };
+template <> struct Vec8<__nv_bfloat16> : Vec8_16<__nv_bfloat16, BF16> {};
+template <> struct Vec8<__half> : Vec8_16<__half, F16> {};
 template <> struct Vec8<float> {
   float4 a, b;
   __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1); }
@@ -528,6 +532,13 @@ __device__ __forceinline__ uint4 affine_relu_vec(uint4 v, const __nv_bfloat162 (
   for (int j = 0; j < 4; ++j) h[j] = __hmax2(__hfma2(h[j], g[j], b[j]), zero);
   return v;
 }
+__device__ __forceinline__ uint4 affine_relu_vec(uint4 v, const __half2 (&g)[4], const __half2 (&b)[4]) {
+  __half2* h = reinterpret_cast<__half2*>(&v);
+  const __half2 zero = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __hmax2(__hfma2(h[j], g[j], b[j]), zero);
+  return v;
+}
 __device__ __forceinline__ uint4 affine_relu_vec(uint4 v, const float (&g)[4], const float (&b)[4]) {
   float* f = reinterpret_cast<float*>(&v);
 #pragma unroll
@@ -541,6 +552,14 @@ template <> struct AffineRegs<__nv_bfloat16> {
     const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c)), bv = __ldg(reinterpret_cast<const uint4*>(beta + c));
 #pragma unroll
     for (int j = 0; j < 4; ++j) { g[j] = reinterpret_cast<const __nv_bfloat162*>(&gv)[j]; b[j] = reinterpret_cast<const __nv_bfloat162*>(&bv)[j]; }
+  }
+};
+template <> struct AffineRegs<__half> {
+  __half2 g[4], b[4];
+  __device__ __forceinline__ void load(const __half* gamma, const __half* beta, int c) {
+    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c)), bv = __ldg(reinterpret_cast<const uint4*>(beta + c));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { g[j] = reinterpret_cast<const __half2*>(&gv)[j]; b[j] = reinterpret_cast<const __half2*>(&bv)[j]; }
   }
 };
 template <> struct AffineRegs<float> {
@@ -751,7 +770,7 @@ int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int
   const int64_t nchunks = (int64_t)B * T2 * F2 * 9;
   if (nchunks == 0) return 0;
   const int grid = pick_grid(nchunks, 8 * 8, 148 * 16);
-  const int esz = dtype == BF16 ? 2 : 4;
+  const int esz = dtype_size(dtype);
   const bool vec = ((C * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(y1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(col) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
   const bool one = vec && C * esz == 32 * 16;

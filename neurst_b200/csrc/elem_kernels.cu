@@ -10,7 +10,14 @@ namespace b200st {
   do {                                                               \
     if ((dt) == F32) { using T = float; __VA_ARGS__; }               \
     else if ((dt) == BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((dt) == F16) { using T = __half; __VA_ARGS__; }         \
     else B200ST_FAIL("bad dtype");                                   \
+  } while (0)
+// three tensors that are either all fp32 or all the same 16-bit type (keeps the instantiation count linear)
+#define DISPATCH_UNIFORM3(d0, d1, d2, T, ...)                                                 \
+  do {                                                                                        \
+    if ((d0) != (d1) || (d1) != (d2)) B200ST_FAIL("the three tensors must share one dtype"); \
+    DISPATCH_DTYPE(d0, T, __VA_ARGS__);                                                       \
   } while (0)
 
 static inline int grid_for(int64_t work, int per_block, int cap = 148 * 16) {
@@ -26,22 +33,24 @@ template <> __device__ __forceinline__ void load4<float>(const float* p, float (
   const float4 a = *reinterpret_cast<const float4*>(p);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
-template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+template <int DT> __device__ __forceinline__ void load4_16(const void* p, float (&v)[4]) {
   const uint2 pk = *reinterpret_cast<const uint2*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  const float2 a = unpack2_16(pk.x, DT), b = unpack2_16(pk.y, DT);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) { load4_16<BF16>(p, v); }
+template <> __device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) { load4_16<F16>(p, v); }
 template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
 template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
-template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+template <int DT> __device__ __forceinline__ void store4_16(void* p, const float (&v)[4]) {
   uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.x = pack2_16(v[0], v[1], DT); pk.y = pack2_16(v[2], v[3], DT);
   *reinterpret_cast<uint2*>(p) = pk;
 }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) { store4_16<BF16>(p, v); }
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float (&v)[4]) { store4_16<F16>(p, v); }
 
 // =============================================================================================
 // LayerNorm forward: one warp per row, values cached in registers for cols <= 1024
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const TDY* __restric
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ dres, TDX* __restrict__ dx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
-                                                          int cols, int relu, void* __restrict__ dnext, int dnext_bf16,
+                                                          int cols, int relu, void* __restrict__ dnext, int dnext_dt,
                                                           const DropoutSpec ndrop) {
   pdl_wait();
   pdl_trigger();
@@ -308,7 +317,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(const TDY* __restric
             const float nscale = ndrop.p > 0.f ? ndrop.scale : 1.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = ((kb[r][i] >> ((c & 4) + j)) & 1u) ? o[j] * nscale : 0.f;
-            if (dnext_bf16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dnext) + row * cols + c, o);
+            if (dnext_dt == BF16) store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dnext) + row * cols + c, o);
+            else if (dnext_dt == F16) store4<__half>(reinterpret_cast<__half*>(dnext) + row * cols + c, o);
             else store4<float>(reinterpret_cast<float*>(dnext) + row * cols + c, o);
           }
         }
@@ -355,16 +365,16 @@ int layernorm_bwd_next(const void* dy, int dy_dtype, const void* x, int x_dtype,
   const int grid = grid_for(rows, 8 * 2, 148 * 8);      // 2 rows in flight per warp; long inputs loop
   const size_t smem = 2 * (size_t)cols * sizeof(float);
 #define LN_BWD_LAUNCH(CPL)                                                                                              \
-  DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
-      (launch_pdl(ln_bwd_kernel<TDY, TX, TDX, CPL>, grid, 256, smem, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
-                                                                (TDX*)dx, dgamma, dbeta, rows, cols, relu)))))
+  DISPATCH_UNIFORM3(dy_dtype, x_dtype, dx_dtype, TT,                                                                    \
+      (launch_pdl(ln_bwd_kernel<TT, TT, TT, CPL>, grid, 256, smem, s, (const TT*)dy, (const TT*)x, mean, rstd, gamma, beta, dres, \
+                                                                (TT*)dx, dgamma, dbeta, rows, cols, relu)))
   const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!dres || (reinterpret_cast<uintptr_t>(dres) & 15) == 0);
 #define LN_BWD_VEC(NV, RR)                                                                                                \
-  DISPATCH_DTYPE(dy_dtype, TDY, DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(dx_dtype, TDX,                               \
-      (launch_pdl(ln_bwd_vec_kernel<TDY, TX, TDX, NV, RR>, grid, 256, smem * 8, s, (const TDY*)dy, (const TX*)x, mean, rstd, gamma, beta, dres, \
-                                                                   (TDX*)dx, dgamma, dbeta, rows, cols, relu, fused_next ? dnext : nullptr, dnext_dtype == BF16 ? 1 : 0, ndrop)))))
+  DISPATCH_UNIFORM3(dy_dtype, x_dtype, dx_dtype, TT,                                                                    \
+      (launch_pdl(ln_bwd_vec_kernel<TT, TT, TT, NV, RR>, grid, 256, smem * 8, s, (const TT*)dy, (const TT*)x, mean, rstd, gamma, beta, dres, \
+                                                                   (TT*)dx, dgamma, dbeta, rows, cols, relu, fused_next ? dnext : nullptr, dnext_dtype, ndrop)))
   const bool vec_ok = vec && ((reinterpret_cast<uintptr_t>(dgamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dbeta) & 15) == 0);
   const bool fused_next = dnext && vec_ok && cols <= 512 && ((reinterpret_cast<uintptr_t>(dnext) & 15) == 0) &&
                           (ndrop.p <= 0.f || ndrop.bits != nullptr);      // on-the-fly Philox sites use the separate kernel
@@ -405,25 +415,27 @@ template <> __device__ __forceinline__ void store8<float>(float* dst, const floa
   *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[8]) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+template <int DT> __device__ __forceinline__ void store8_16(void* dst, const float (&v)[8]) {
   uint4 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-  pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  pk.x = pack2_16(v[0], v[1], DT); pk.y = pack2_16(v[2], v[3], DT);
+  pk.z = pack2_16(v[4], v[5], DT); pk.w = pack2_16(v[6], v[7], DT);
   *reinterpret_cast<uint4*>(dst) = pk;
 }
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[8]) { store8_16<BF16>(dst, v); }
+template <> __device__ __forceinline__ void store8<__half>(__half* dst, const float (&v)[8]) { store8_16<F16>(dst, v); }
 template <typename T> __device__ __forceinline__ void load8(const T* src, float (&v)[8]);
 template <> __device__ __forceinline__ void load8<float>(const float* src, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[8]) {
+template <int DT> __device__ __forceinline__ void load8_16(const void* src, float (&v)[8]) {
   const uint4 pk = *reinterpret_cast<const uint4*>(src);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+  const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  for (int i = 0; i < 4; ++i) { const float2 f = unpack2_16(w[i], DT); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[8]) { load8_16<BF16>(src, v); }
+template <> __device__ __forceinline__ void load8<__half>(const __half* src, float (&v)[8]) { load8_16<F16>(src, v); }
 
 template <typename T, int STEPS>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, int64_t ldS,
@@ -651,7 +663,7 @@ __global__ void colsum_kernel(const T* __restrict__ dY, int64_t M, int N, int64_
 }
 int colsum_accum(const void* dY, int dtype, int64_t M, int N, int64_t ld, float* db, cudaStream_t s) {
   if (M == 0 || N == 0) return 0;
-  const int esz = dtype == BF16 ? 2 : 4;
+  const int esz = dtype_size(dtype);
   const bool vec = (N % 8 == 0) && ((ld * esz) % (8 * esz) == 0) && ((reinterpret_cast<uintptr_t>(dY) & (8 * esz - 1)) == 0);
   if (vec) {
     const int gx = ceil_div(N, 256);
@@ -826,9 +838,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) lsce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ trg,
                                                     const int64_t* __restrict__ trg_length, int B, int L, int V,
                                                     float eps_ls, float* __restrict__ nll_sum, T* __restrict__ dlogits,
-                                                    float loss_scale) {
+                                                    float loss_scale, const float* __restrict__ loss_scale_dev) {
   pdl_wait();
   pdl_trigger();
+  if (loss_scale_dev) loss_scale *= *loss_scale_dev;
   __shared__ float sm[32];
   const int64_t row = blockIdx.x;
   const int b = (int)(row / L), l = (int)(row % L);
@@ -872,9 +885,10 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256) lsce_vec_kernel(const float* __restrict__ logits, const int64_t* __restrict__ trg,
                                                         const int64_t* __restrict__ trg_length, int B, int L, int V,
                                                         float eps_ls, float* __restrict__ nll_sum, T* __restrict__ dlogits,
-                                                        float loss_scale) {
+                                                        float loss_scale, const float* __restrict__ loss_scale_dev) {
   pdl_wait();
   pdl_trigger();
+  if (loss_scale_dev) loss_scale *= *loss_scale_dev;
   __shared__ float sm[32];
   const int64_t row = blockIdx.x;
   const int b = (int)(row / L), l = (int)(row % L);
@@ -954,19 +968,19 @@ __global__ void lsce_finalize_kernel(const float* __restrict__ nll_sum, const in
 
 int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_length, int B, int L, int V,
                  float label_smoothing, float* nll_sum, float* n_tokens, float* loss, void* dlogits, int d_dtype,
-                 float loss_scale, cudaStream_t s) {
+                 float loss_scale, const float* loss_scale_dev, cudaStream_t s) {
   if (B * L == 0) return 0;
   B200ST_CUDA(cudaMemsetAsync(nll_sum, 0, sizeof(float) * B, s));
   const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) && (!dlogits || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0);
   if (vec && V <= 8192)
     DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_vec_kernel<T, 8>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing,
-                                           nll_sum, (T*)dlogits, loss_scale)));
+                                           nll_sum, (T*)dlogits, loss_scale, loss_scale_dev)));
   else if (vec && V <= 32768)
     DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_vec_kernel<T, 32>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing,
-                                           nll_sum, (T*)dlogits, loss_scale)));
+                                           nll_sum, (T*)dlogits, loss_scale, loss_scale_dev)));
   else
     DISPATCH_DTYPE(d_dtype, T, (launch_pdl(lsce_kernel<T>, B * L, 256, 0, s, logits, trg, trg_length, B, L, V, label_smoothing, nll_sum,
-                                           (T*)dlogits, loss_scale)));
+                                           (T*)dlogits, loss_scale, loss_scale_dev)));
   B200ST_LAUNCH_CHECK();
   launch_pdl(lsce_finalize_kernel, 1, 256, 0, s, nll_sum, trg_length, B, L, n_tokens, loss);
   g_kernel_launches += 2;
@@ -974,59 +988,6 @@ int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_len
   return 0;
 }
 
-// =============================================================================================
-// optimizer / parameter utilities
-// =============================================================================================
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            __nv_bfloat16* __restrict__ shadow, int64_t n, float lr_t, float b1, float b2, float eps,
-                            float gscale, int zero_grad) {
-  pdl_wait();
-  pdl_trigger();
-  // 16-byte accesses (all arenas are 256-byte aligned); scalar tail for n % 4
-  const int64_t n4 = n >> 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 g4 = reinterpret_cast<const float4*>(g)[i], m4 = reinterpret_cast<const float4*>(m)[i];
-    const float4 v4 = reinterpret_cast<const float4*>(v)[i], p4 = reinterpret_cast<const float4*>(p)[i];
-    const float gi[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
-    const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w}, po[4] = {p4.x, p4.y, p4.z, p4.w};
-    float mi[4], vi[4], pi[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mi[j] = b1 * mo[j] + (1.f - b1) * gi[j];
-      vi[j] = b2 * vo[j] + (1.f - b2) * gi[j] * gi[j];
-      pi[j] = po[j] - lr_t * mi[j] / (sqrtf(vi[j]) + eps);
-    }
-    reinterpret_cast<float4*>(m)[i] = make_float4(mi[0], mi[1], mi[2], mi[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(vi[0], vi[1], vi[2], vi[3]);
-    reinterpret_cast<float4*>(p)[i] = make_float4(pi[0], pi[1], pi[2], pi[3]);
-    if (shadow) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(pi[0], pi[1]), h1 = __floats2bfloat162_rn(pi[2], pi[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      reinterpret_cast<uint2*>(shadow)[i] = pk;
-    }
-    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
-    m[i] = mi; v[i] = vi; p[i] = pi;
-    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
-    if (zero_grad) g[i] = 0.f;
-  }
-}
-int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
-              float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s) {
-  if (n == 0) return 0;
-  B200ST_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(shadow) & 7) == 0, "adam: arenas must be 16-byte aligned");
-  launch_pdl(adam_kernel, grid_for(n, 256 * 4 * 4), 256, 0, s, p, g, m, v, shadow, n, lr_t, beta1, beta2, eps, grad_scale, zero_grad);
-  ++g_kernel_launches;
-  B200ST_LAUNCH_CHECK();
-  return 0;
-}
 __global__ void dropout_bits_kernel(DropoutSpec drop, int64_t ngroups, uint8_t* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
@@ -1075,19 +1036,6 @@ __global__ void __launch_bounds__(256) dropout_bits_multi_kernel(const DropBitsT
 int dropout_bits_multi(const DropBitsTable& t, uint64_t seed, const uint64_t* seed_ptr, uint8_t* base, cudaStream_t s) {
   if (t.n == 0 || t.goff[t.n] == 0) return 0;
   launch_pdl(dropout_bits_multi_kernel, grid_for((t.goff[t.n] + 3) / 4, 256, 148 * 8), 256, 0, s, t, seed, seed_ptr, base);
-  ++g_kernel_launches;
-  B200ST_LAUNCH_CHECK();
-  return 0;
-}
-__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
-  pdl_wait();
-  pdl_trigger();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = __float2bfloat16_rn(x[i]);
-}
-int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s) {
-  if (n == 0) return 0;
-  launch_pdl(cast_bf16_kernel, grid_for(n, 256 * 4), 256, 0, s, x, y, n);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

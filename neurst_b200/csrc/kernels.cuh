@@ -58,11 +58,34 @@ int padding_to_bias(const float* padding, float* bias, int64_t n, cudaStream_t s
 // dlogits(dtype)[B*L, V] = w/sum_tokens * loss_scale * (softmax - soft_target)
 int lsce_fwd_bwd(const float* logits, const int64_t* trg, const int64_t* trg_length, int B, int L, int V,
                  float label_smoothing, float* nll_sum, float* n_tokens, float* loss, void* dlogits, int d_dtype,
-                 float loss_scale, cudaStream_t s);
+                 float loss_scale, const float* loss_scale_dev, cudaStream_t s);
 
-// Keras Adam (epsilon-hat form) over a flat arena; optionally refreshes the bf16 shadow and zeroes g.
-int adam_step(float* p, float* g, float* m, float* v, __nv_bfloat16* shadow, int64_t n, float lr_t, float beta1,
-              float beta2, float eps, float grad_scale, int zero_grad, cudaStream_t s);
+// ---- optimizer step (optim.cu) --------------------------------------------------------------------------------------
+// Offsets of the parameter tensors inside the flat arena (each a multiple of 8 elements; tensor i = [off[i], off[i+1]))
+// travel as a kernel argument: per-tensor gradient norms and the per-tensor clip need no device-side table.
+struct TensorTable {
+  int n;
+  uint32_t off8[513];      // offsets / 8
+};
+// Device-resident control block of the step (6 floats), caller-owned:
+//   [0] loss scale S (fp16 precision: the loss gradient was multiplied by S)   [1] consecutive finite steps
+//   [2] 1 when the LAST step was skipped (non-finite gradients)                [3] number of skipped steps so far
+//   [4] number of applied steps (Adam's t)                                      [5] global gradient norm of the last step
+struct OptimArgs {
+  float* p; float* g; float* m; float* v;
+  void* shadow; int shadow_dtype;     // 16-bit copy of the arena refreshed in the same pass (or null)
+  int64_t n;
+  float lr, beta1, beta2, eps;
+  int64_t step_t;                     // Adam's t when `ctl` is null (host-counted); with `ctl` t = ctl[4] + 1
+  float grad_scale;                   // 1 / (replicas * update_cycle)
+  int zero_grad;
+  float clip_value, clip_norm;        // <= 0: off.  tf.clip_by_value / tf.clip_by_norm PER TENSOR (gradaccum_keras_model.py:228-233)
+  float* tensor_sumsq;                // [n_tensors + 1] scratch (needed for clip_norm or ctl); last = total
+  float* ctl;                         // dynamic loss scale state or null
+  float growth_steps, multiplier;     // revised_dynamic_loss_scale.py:82-107 (2000, 2)
+};
+int optimizer_step(const OptimArgs& a, const TensorTable& tt, cudaStream_t s);
+int cast_f32_to_16(const float* x, void* y, int y_dtype, int64_t n, cudaStream_t s);
 // out[g] = keep-bits of elements [8g, 8g+8) of the dropout site (identical to the on-the-fly Philox decisions)
 int dropout_bits(DropoutSpec drop, int64_t n_elems, uint8_t* out, cudaStream_t s);
 // all dropout sites of a step in one launch: site i covers groups [goff[i], goff[i+1]) and writes base[boff[i] + local]
@@ -74,16 +97,15 @@ struct DropBitsTable {
   int64_t boff[128];
 };
 int dropout_bits_multi(const DropBitsTable& t, uint64_t seed, const uint64_t* seed_ptr, uint8_t* base, cudaStream_t s);
-int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, int64_t n, cudaStream_t s);
 int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 
-// ---- fused attention (bf16, head dim 64): tcgen05 QK^T / PV with on-chip online softmax (attention.cu) ----
+// ---- fused attention (16-bit operand type `dt` = BF16 or F16, head dim 64): tcgen05 QK^T / PV with on-chip online softmax (attention.cu) ----
 // q/k/v/ctx/dctx/dq/dk/dv: bf16 views [B*T, ld], head h at columns [h*64, h*64+64); bias fp32 [B,Tk] or null;
 // lse fp32 [B,H,Tq] (written by forward, read by backward); dq_scratch fp32 [B*Tq, H*64] followed by [B*H*Tq] floats (rowsum(dO*O)).
-int attention_fwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
+int attention_fwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
                         int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
                         cudaStream_t s);
-int attention_bwd_fused(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
+int attention_bwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
                         int64_t ctx_ld, const void* dctx, int64_t dctx_ld, const float* lse, int B, int H, int Tq, int Tk,
                         const float* bias, int causal, DropoutSpec drop, float* dq_scratch, void* dq, int64_t dq_ld, void* dk,
                         int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s);

@@ -47,8 +47,8 @@ static void add_ffn(Model& m, const std::string& pre, int d, int ffn) {
 int build_param_table(Model& m) {
   const Config& c = m.cfg;
   m.params.clear(); m.index.clear(); m.arena_numel = 0;
-  m.adt = c.precision == BF16 ? BF16 : F32;
-  B200ST_CHECK(c.precision == F32 || c.precision == BF16, "precision must be 0 (fp32) or 1 (bf16)");
+  B200ST_CHECK(c.precision == F32 || c.precision == BF16 || c.precision == F16, "precision must be 0 (fp32), 1 (bf16) or 2 (fp16)");
+  m.adt = c.precision;
   if (c.model_type == MODEL_MHA) {
     B200ST_CHECK(c.heads > 0 && c.d % c.heads == 0, "num_units must be divisible by heads");
     add_attention(m, "att", !c.mha_self, c.mha_din, c.mha_dmem, c.d, c.mha_dout, false);
@@ -86,7 +86,7 @@ int build_param_table(Model& m) {
   if (c.model_type == MODEL_SPEECH || c.model_type == MODEL_TEXT) {
     add_param(m, "trg.emb", {c.vocab, c.d}); add_param(m, "trg.bias", {c.vocab});
   }
-  if (c.precision == BF16) {
+  if (is16(c.precision)) {
     B200ST_CHECK(c.d % 8 == 0 && c.ffn % 8 == 0 && (c.d / c.heads) % 8 == 0, "bf16 mode needs d, ffn, head dim % 8 == 0");
     if (c.model_type == MODEL_SPEECH) B200ST_CHECK(c.channels % 8 == 0, "bf16 mode needs channels % 8 == 0");
     if (c.model_type <= MODEL_TEXT) B200ST_CHECK(c.vocab % 8 == 0, "bf16 mode needs vocab % 8 == 0");
@@ -223,7 +223,7 @@ struct Ctx {
     ar.base = reinterpret_cast<char*>(b.workspace);
     ar.cap = b.workspace_bytes;
   }
-  size_t esz() const { return adt == BF16 ? 2 : 4; }
+  size_t esz() const { return (size_t)dtype_size(adt); }
   void* act(int64_t n) { return ar.take((size_t)n * esz()); }
   float* f32(int64_t n) { return reinterpret_cast<float*>(ar.take((size_t)n * 4)); }
   std::unordered_map<uint64_t, DropoutSpec> drop_memo;
@@ -267,7 +267,7 @@ struct Ctx {
     const ParamInfo* p = info(n);
     GemmOperand o{};
     if (!p) return o;
-    if (adt == BF16) { o.ptr = buf.shadow + p->offset; o.dtype = BF16; }
+    if (is16(adt)) { o.ptr = reinterpret_cast<const uint16_t*>(buf.shadow) + p->offset; o.dtype = adt; }
     else { o.ptr = buf.params + p->offset; o.dtype = F32; }
     o.mn_major = mn_major; o.ld = ld;
     return o;
@@ -347,13 +347,13 @@ static GemmOperand head_op(const Ctx& c, View v, int T, int dh, int mn_major) {
 static int round8(int x) { return (x + 7) / 8 * 8; }
 
 static bool use_fused_attention(const Ctx& c, const AttnDims& a) {
-  return c.adt == BF16 && a.units / a.H == 64 && !c.m.cfg.disable_fused_attention;
+  return is16(c.adt) && a.units / a.H == 64 && !c.m.cfg.disable_fused_attention;
 }
 
 static int attention_fwd(Ctx& c, const AttnDims& a, View q, View k, View v, const float* bias, int causal, DropoutSpec drop,
                          float* S, void* p_pre, void* p_drop, void* ctx, float* lse) {
   if (use_fused_attention(c, a)) {
-    RUN(attention_fwd_fused(q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, a.B, a.H, a.Tq, a.Tk, bias, causal, drop, ctx, a.units, lse, c.st));
+    RUN(attention_fwd_fused(c.adt, q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, a.B, a.H, a.Tq, a.Tk, bias, causal, drop, ctx, a.units, lse, c.st));
     return 0;
   }
   const int dh = a.units / a.H, Tkp = round8(a.Tk);
@@ -379,7 +379,7 @@ static int attention_bwd(Ctx& c, const AttnDims& a, View q, View k, View v, cons
                          DropoutSpec drop, const void* dctx, float* dP, void* dS, View dq, View dk, View dv, const void* ctx,
                          const float* lse, const float* bias, int causal, float* dq32) {
   if (use_fused_attention(c, a)) {
-    RUN(attention_bwd_fused(q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, ctx, a.units, dctx, a.units, lse, a.B, a.H, a.Tq, a.Tk, bias, causal,
+    RUN(attention_bwd_fused(c.adt, q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, ctx, a.units, dctx, a.units, lse, a.B, a.H, a.Tq, a.Tk, bias, causal,
                             drop, dq32, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, c.st));
     return 0;
   }
@@ -865,7 +865,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   c.seed = b.seed;
   c.seed_dev = b.seed_dev;
   if (backward) B200ST_CHECK(c.buf.grads != nullptr && b.trg != nullptr && b.trg_length != nullptr, "backward needs grads and targets");
-  if (c.adt == BF16) B200ST_CHECK(c.buf.shadow != nullptr, "bf16 precision needs the bf16 shadow arena");
+  if (is16(c.adt)) B200ST_CHECK(c.buf.shadow != nullptr, "16-bit precision needs the 16-bit shadow arena");
 
   Scratch sc;
   alloc_scratch(c, sc, B, Ts > L ? Ts : L, Ts > L ? Ts : L, Ms > Md ? Ms : Md, Ms, backward);
@@ -914,7 +914,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
     float* loss = b.loss ? b.loss : c.f32(1);
     if (backward) dlogits = c.act((int64_t)Md * V);
     RUN(lsce_fwd_bwd(logits, b.trg, b.trg_length, B, L, V, cf.label_smoothing, nll, ntok, loss, dlogits, c.adt,
-                     b.loss_scale > 0.f ? b.loss_scale : 1.f, c.st));
+                     b.loss_scale > 0.f ? b.loss_scale : 1.f, b.loss_scale_dev, c.st));
   }
   if (!backward) return 0;
 
@@ -969,7 +969,7 @@ static int run_planned(const Model& m, const Buffers& buf, cudaStream_t st, F&& 
   static char dummy[64];
   Buffers fake = buf;
   if (!fake.params) fake.params = reinterpret_cast<const float*>(dummy);
-  if (!fake.shadow) fake.shadow = reinterpret_cast<const __nv_bfloat16*>(dummy);
+  if (!fake.shadow) fake.shadow = dummy;
   if (need_out && !fake.grads) fake.grads = reinterpret_cast<float*>(dummy);
   fake.workspace = nullptr; fake.workspace_bytes = 0;
   Ctx dry(m, fake, nullptr, true);
@@ -980,7 +980,7 @@ static int run_planned(const Model& m, const Buffers& buf, cudaStream_t st, F&& 
   B200ST_CHECK((reinterpret_cast<uintptr_t>(buf.workspace) & 255) == 0, "workspace must be 256-byte aligned");
   B200ST_CHECK(buf.workspace_bytes >= need, "workspace too small: need " + std::to_string(need) + " bytes, have " +
                                                 std::to_string(buf.workspace_bytes));
-  if (m.adt == BF16) B200ST_CHECK(buf.shadow != nullptr, "bf16 precision needs the bf16 shadow arena");
+  if (is16(m.adt)) B200ST_CHECK(buf.shadow != nullptr, "16-bit precision needs the 16-bit shadow arena");
   Ctx real(m, buf, st, false);
   // All dropout keep-bits of the call in ONE launch: the planning pass recorded every site in allocation order (the real
   // pass allocates identically), the table travels as a kernel argument.

@@ -17,7 +17,7 @@ struct Config {
   int model_type;
   int d, heads, ffn, enc_layers, dec_layers, vocab, src_vocab;
   int feat, in_channels, channels, conv_layer_norm;
-  int precision;              // F32: fp32 FMA kernels (parity mode); BF16: tcgen05 kernels
+  int precision;              // F32: fp32 FMA kernels (parity mode); BF16 / F16: tcgen05 kernels with that 16-bit type
   float ln_eps, attention_dropout, ffn_dropout, postprocess_dropout, label_smoothing;
   int share_src_trg_embedding;
   // MODEL_MHA only
@@ -51,7 +51,7 @@ int build_param_table(Model& m);
 // Caller-provided device memory for one call.
 struct Buffers {
   const float* params;                 // fp32 master arena
-  const __nv_bfloat16* shadow;         // bf16 copy of the arena (BF16 precision only)
+  const void* shadow;                  // 16-bit copy of the arena in the handle's precision (bf16 / fp16 modes)
   float* grads;                        // fp32 gradient arena (accumulated into; null for inference)
   void* workspace;
   size_t workspace_bytes;
@@ -71,6 +71,7 @@ struct Batch {
   uint64_t seed;
   const uint64_t* seed_dev;            // optional: device-resident seed (overrides `seed`)
   float loss_scale;                    // multiplies dlogits (1/world for DP mean, gradient-accumulation factor, ...)
+  const float* loss_scale_dev;         // optional device word multiplied in as well (dynamic loss scale of the fp16 mode)
   // outputs (device, optional)
   float* logits;                       // fp32 [B,L,V]
   float* loss;                         // [1]

@@ -504,10 +504,10 @@ int g_num_sms = 0;
 int64_t g_launches = 0;
 }  // namespace
 
-// bf16 4-D tensor map (inner, rows, nb1, nb2) with a {box_inner<=64, box_rows} box, 128B swizzle.
-int make_tma_map_bf16(const void* ptr, uint64_t inner, uint64_t rows, int nb1, int nb2, int64_t ld, int64_t sb1, int64_t sb2,
-                      uint32_t box_rows, CUtensorMap* out) {
-  GemmOperand op{ptr, BF16, 0, ld, sb1, sb2};
+// 16-bit 4-D tensor map (inner, rows, nb1, nb2) with a {box_inner<=64, box_rows} box, 128B swizzle.
+int make_tma_map_16(const void* ptr, int dtype, uint64_t inner, uint64_t rows, int nb1, int nb2, int64_t ld, int64_t sb1, int64_t sb2,
+                    uint32_t box_rows, CUtensorMap* out) {
+  GemmOperand op{ptr, dtype, 0, ld, sb1, sb2};
   return make_operand_map(op, (int)rows, (int)inner, nb1, nb2, (int)box_rows, out);
 }
 void tc_count_launch() { ++g_launches; }

@@ -45,6 +45,40 @@ def speech_transformer_hparams(name):
     }
 
 
+def _model_flags(speech):
+    """(name, python type, default, help) of every `model.params` key — the flag list of the reference's
+    `class_or_method_args()` (neurst_pt/models/speech_transformer.py:35-106, neurst/models/transformer.py:45-120):
+    same names and defaults, so `registry.build_x` fills a user's partial params dict exactly as for the reference class."""
+    fl = [("modality.share_embedding_and_softmax_weights", bool, False,
+           "Whether to share the target embedding table and softmax weights."),
+          ("modality.dim", int, None, "The default embedding dimension for both source and target side."),
+          ("modality.source.dim", int, None, "The source-side embedding dimension, or `modality.dim` if not provided."),
+          ("modality.target.dim", int, None, "The target-side embedding dimension, or `modality.dim` if not provided."),
+          ("modality.timing", str, None, "The positional encoding of both source and target side."),
+          ("modality.source.timing", str, None, "The source-side positional encoding, or `modality.timing`."),
+          ("modality.target.timing", str, None, "The target-side positional encoding, or `modality.timing`.")]
+    if speech:
+        fl += [("modality.source.kernel_size", int, 3, "The kernel size for the first two conv layer"),
+               ("modality.source.strides", int, 2, "The stride size for the first two conv layer"),
+               ("modality.source.channels", int, 256, "The channels for the first two conv layer"),
+               ("modality.source.layer_norm", bool, False, "Whether to apply layer norm in convolution layers.")]
+    else:
+        fl += [("modality.share_source_target_embedding", bool, False,
+                "Whether to share source and target embedding table.")]
+    for side in ("encoder", "decoder"):
+        fl += [(side + ".num_layers", int, None, "The number of stacking layers of the %s." % side),
+               (side + ".hidden_size", int, None, "The number of hidden units of the %s." % side),
+               (side + ".num_attention_heads", int, None, "The number of attention heads of the %s." % side),
+               (side + ".filter_size", int, None, "The filter size of the %s ffn." % side),
+               (side + ".ffn_activation", str, "relu", "The activation function of the %s ffn layer." % side),
+               (side + ".attention_dropout_rate", float, 0., "The dropout rate of the %s attention layers." % side),
+               (side + ".attention_type", str, "dot_product", "The type of the attention function of the %s." % side),
+               (side + ".ffn_dropout_rate", float, 0., "The dropout rate of the %s ffn layer." % side),
+               (side + ".layer_postprocess_dropout_rate", float, 0., "The dropout rate of each layer's post process."),
+               (side + ".layer_postprocess_epsilon", float, 1e-6, "The epsilon for layer normalization in the %s." % side)]
+    return fl
+
+
 def _check_supported(args, speech):
     def same(a, b):
         return args.get(a) == args.get(b)
@@ -54,10 +88,14 @@ def _check_supported(args, speech):
                                                                        "decoder.num_attention_heads")
             and same("encoder.filter_size", "decoder.filter_size")):
         raise NotImplementedError("libb200st needs identical encoder/decoder hidden, heads and filter sizes")
-    if args.get("modality.dim") != args.get("encoder.hidden_size"):
-        raise NotImplementedError("modality.dim must equal the hidden size")
-    if (args.get("modality.timing") or args.get("modality.target.timing")) != "sinusoids":
-        raise NotImplementedError("only sinusoid position signals are supported")
+    for k in ("modality.dim", "modality.source.dim", "modality.target.dim"):
+        if args.get(k) is not None and args.get(k) != args.get("encoder.hidden_size"):
+            raise NotImplementedError("%s must equal the hidden size" % k)
+    if args.get("modality.dim") is None and args.get("modality.target.dim") is None:
+        raise NotImplementedError("modality.dim must be given (and equal the hidden size)")
+    for side in ("source", "target"):
+        if (args.get("modality.%s.timing" % side) or args.get("modality.timing")) != "sinusoids":
+            raise NotImplementedError("only sinusoid position signals are supported")
     if not args.get("modality.share_embedding_and_softmax_weights", False):
         raise NotImplementedError("the output layer must share the target embedding (all reference presets do)")
     for side in ("encoder", "decoder"):

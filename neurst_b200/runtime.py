@@ -11,6 +11,12 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# "mixed16" = the reference's mixed precision (fp16 compute + dynamic loss scaling, training_utils.py:73-81) = "fp16"
+PRECISIONS = {"fp32": L.F32, "float32": L.F32, "bf16": L.BF16, "bfloat16": L.BF16, "fp16": L.F16, "float16": L.F16,
+              "mixed16": L.F16, "mixed_float16": L.F16}
+_TORCH16 = {L.BF16: torch.bfloat16, L.F16: torch.float16}
+
+
 def make_config(model_type, d, heads, ffn=0, enc_layers=0, dec_layers=0, vocab=0, src_vocab=0, feat=80, in_channels=1,
                 channels=0, conv_layer_norm=True, precision="bf16", ln_eps=1e-6, attention_dropout=0.0, ffn_dropout=0.0,
                 postprocess_dropout=0.0, label_smoothing=0.0, share_src_trg_embedding=False, mha_self=False, mha_din=0,
@@ -20,7 +26,7 @@ def make_config(model_type, d, heads, ffn=0, enc_layers=0, dec_layers=0, vocab=0
     c.d, c.heads, c.ffn, c.enc_layers, c.dec_layers = d, heads, ffn, enc_layers, dec_layers
     c.vocab, c.src_vocab = vocab, src_vocab
     c.feat, c.in_channels, c.channels, c.conv_layer_norm = feat, in_channels, channels, int(conv_layer_norm)
-    c.precision = {"fp32": L.F32, "float32": L.F32, "bf16": L.BF16, "bfloat16": L.BF16}[precision]
+    c.precision = PRECISIONS[precision]
     c.ln_eps = ln_eps
     c.attention_dropout, c.ffn_dropout, c.postprocess_dropout = attention_dropout, ffn_dropout, postprocess_dropout
     c.label_smoothing = label_smoothing
@@ -43,7 +49,9 @@ class Runtime:
         h = C.c_void_p()
         L.check(self.lib.b200st_create(C.byref(config), C.byref(h)))
         self.handle = h
-        self.bf16 = config.precision == L.BF16
+        self.prec = int(config.precision)
+        self.bf16 = self.prec in _TORCH16          # (historic name) any 16-bit tensor-core precision
+        self.fp16 = self.prec == L.F16
         self.numel = int(self.lib.b200st_param_arena_numel(h))
         self.table = {}
         name = C.create_string_buffer(128)
@@ -52,7 +60,14 @@ class Runtime:
             L.check(self.lib.b200st_param_info(h, i, name, 128, C.byref(off), C.byref(nd), shp))
             self.table[name.value.decode()] = (int(off.value), tuple(int(shp[k]) for k in range(nd.value)))
         self.params = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
-        self.shadow = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device) if self.bf16 else None
+        self.shadow = torch.zeros(self.numel, dtype=_TORCH16[self.prec], device=self.device) if self.bf16 else None
+        # dynamic loss scale state of the fp16 precision (b200st_optimizer_step): scale starts at 2^15 like the reference
+        # (training_utils.py:413-416); float[8] on the device so CUDA-graph replays follow it
+        self.loss_scale_state = None
+        self.tensor_sumsq = None
+        if self.fp16:
+            self.loss_scale_state = torch.zeros(8, dtype=torch.float32, device=self.device)
+            self.loss_scale_state[0] = 2.0 ** 15
         self.grads = None
         self.adam_m = None
         self.adam_v = None
@@ -89,7 +104,7 @@ class Runtime:
 
     def refresh_shadow(self):
         if self.bf16:
-            L.check(self.lib.b200st_refresh_shadow(_ptr(self.params), _ptr(self.shadow), self.numel, L._stream()))
+            L.check(self.lib.b200st_refresh_shadow(_ptr(self.params), _ptr(self.shadow), self.prec, self.numel, L._stream()))
         self._shadow_stale = False
 
     def ensure_grads(self):
@@ -155,6 +170,8 @@ class Runtime:
         bt.training = int(batch.get("training", backward))
         bt.seed = int(batch.get("seed", 0))
         bt.loss_scale = float(batch.get("loss_scale", 1.0))
+        if backward and self.fp16 and batch.get("dynamic_loss_scale", True):
+            bt.loss_scale_dev = self.loss_scale_state.data_ptr()       # gradients come out multiplied by state[0]
         out = {}
         V = self.config.vocab
         if batch.get("want_logits", not backward):
@@ -177,13 +194,37 @@ class Runtime:
         L.check(fn(self.handle, C.byref(bufs), C.byref(bt), L._stream()))
         return out
 
-    def adam_step(self, lr, step_t, beta1=0.9, beta2=0.98, eps=1e-9, grad_scale=1.0, zero_grad=True):
+    def adam_step(self, lr, step_t, beta1=0.9, beta2=0.98, eps=1e-9, grad_scale=1.0, zero_grad=True, clip_value=None,
+                  clip_norm=None, dynamic_loss_scale=None, growth_steps=2000, multiplier=2.0):
+        """One optimizer step over the flat arenas (b200st_optimizer_step): unscale -> clip (per gradient tensor, as
+        tf.clip_by_value / tf.clip_by_norm in gradaccum_keras_model.py:228-233) -> Keras Adam -> shadow refresh -> g = 0.
+        fp16 precision: the gradients carry the dynamic loss scale; a step with non-finite gradients is skipped on the
+        device (state in `self.loss_scale_state`)."""
         if self.adam_m is None:
             self.adam_m = torch.zeros_like(self.params)
             self.adam_v = torch.zeros_like(self.params)
-        L.check(self.lib.b200st_adam_step(_ptr(self.params), _ptr(self.ensure_grads()), _ptr(self.adam_m), _ptr(self.adam_v),
-                                          _ptr(self.shadow), self.numel, lr, beta1, beta2, eps, int(step_t), grad_scale,
-                                          int(zero_grad), L._stream()))
+        dyn = self.fp16 if dynamic_loss_scale is None else bool(dynamic_loss_scale)
+        a = L.OptimArgs()
+        a.params, a.grads = self.params.data_ptr(), self.ensure_grads().data_ptr()
+        a.m, a.v = self.adam_m.data_ptr(), self.adam_v.data_ptr()
+        a.shadow = self.shadow.data_ptr() if self.bf16 else None
+        a.shadow_dtype = self.prec if self.bf16 else L.BF16
+        a.numel = self.numel
+        a.lr, a.beta1, a.beta2, a.eps = lr, beta1, beta2, eps
+        a.step_t, a.grad_scale, a.zero_grad = int(step_t), grad_scale, int(zero_grad)
+        a.clip_value = float(clip_value or 0.0)
+        a.clip_norm = float(clip_norm or 0.0)
+        if dyn or a.clip_norm > 0:
+            if self.tensor_sumsq is None:
+                self.tensor_sumsq = torch.zeros(len(self.table) + 1, dtype=torch.float32, device=self.device)
+            a.tensor_sumsq = self.tensor_sumsq.data_ptr()
+        if dyn:
+            if self.loss_scale_state is None:
+                self.loss_scale_state = torch.zeros(8, dtype=torch.float32, device=self.device)
+                self.loss_scale_state[0] = 1.0
+            a.loss_scale_state = self.loss_scale_state.data_ptr()
+            a.growth_steps, a.multiplier = float(growth_steps), float(multiplier)
+        L.check(self.lib.b200st_optimizer_step(self.handle, C.byref(a), L._stream()))
         self._shadow_stale = False
 
     def dropout_mask(self, site, n, p, seed):
@@ -226,6 +267,8 @@ class GraphedTrainStep:
         bt.trg_input, bt.trg, bt.trg_length = self.trg_input.data_ptr(), self.trg.data_ptr(), self.trg_length.data_ptr()
         bt.B, bt.T, bt.L, bt.training = B, T, Lq, 1
         bt.seed, bt.seed_dev, bt.loss_scale = 0, self.seed.data_ptr(), 1.0
+        if rt.fp16:
+            bt.loss_scale_dev = rt.loss_scale_state.data_ptr()
         bt.loss, bt.nll_sum, bt.n_tokens = self.loss.data_ptr(), self.nll_sum.data_ptr(), self.n_tokens.data_ptr()
         self.bt = bt
         self.graph = None

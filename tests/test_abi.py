@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
-    assert lib.b200st_version() >= 100
+    assert lib.b200st_version() == L.ABI_VERSION
 
 
 def test_parameter_table_matches_reference_layouts():
@@ -69,7 +69,7 @@ def test_struct_layouts_match_the_c_header(tmp_path):
     import ctypes as C
     import subprocess
     pairs = [("b200st_operand", L.Operand), ("b200st_gemm_args", L.GemmArgs), ("b200st_config", L.Config),
-             ("b200st_buffers", L.Buffers), ("b200st_batch", L.Batch)]
+             ("b200st_buffers", L.Buffers), ("b200st_batch", L.Batch), ("b200st_optim_args", L.OptimArgs)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200st.h"', 'int main(void) {']
     for cname, cls in pairs:
         lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))

@@ -45,7 +45,9 @@ def _run_case(hp, B, T, Lq, precision, dropout, seed=11):
     e_logits = float((out["logits"].cpu().double() - logits).abs().max())
     e_rms = float((out["logits"].cpu().double() - logits).pow(2).mean().sqrt())
     e_loss = abs(float(out["loss"]) - float(loss))
-    errs = sorted(((U.rel_err(rt.grad_view(k), g), k) for k, g in grads.items()), reverse=True)
+    # fp16 precision: the gradient arena carries the dynamic loss scale (unscaled inside the optimizer step)
+    S = float(rt.loss_scale_state[0]) if rt.fp16 else 1.0
+    errs = sorted(((U.rel_err(rt.grad_view(k) / S, g), k) for k, g in grads.items()), reverse=True)
     print("\n[baseline-shape %s B=%d T=%d L=%d %s p=%.1f] logits max-abs %.3e rms %.3e | loss %.6f vs %.6f (%.2e) | "
           "worst grads %s | oracle %.1fs" % (hp, B, T, Lq, precision, dropout, e_logits, e_rms, float(out["loss"]), float(loss),
                                               e_loss, ", ".join("%s %.2e" % (k, e) for e, k in errs[:3]), t_or))
