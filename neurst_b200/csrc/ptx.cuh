@@ -143,7 +143,7 @@ __device__ __forceinline__ void tmem_alloc_n(uint32_t dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
 }
 // Instruction descriptor for kind::f16: {f16|bf16} x {f16|bf16} -> fp32 (bits 4-5 = 1), A format bits 7-9 and B format
-// bits 10-12 (0 = f16, 1 = bf16; the two operands are converted independently, so mixed products are legal), M = 128.
+// bits 10-12 (0 = f16, 1 = bf16; callers keep both equal: mixed formats fault on B200), M = 128.
 __host__ __device__ __forceinline__ uint32_t make_idesc_16(int n, int a_mn_major, int b_mn_major, int a_bf16, int b_bf16, int m = 128) {
   return (1u << 4) | ((uint32_t)(a_bf16 ? 1 : 0) << 7) | ((uint32_t)(b_bf16 ? 1 : 0) << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

@@ -561,6 +561,9 @@ int64_t tc_launch_count() { return g_launches; }
 
 int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   B200ST_CHECK(is16(g.A.dtype) && is16(g.B.dtype), "tcgen05 GEMM needs 16-bit (bf16 / fp16) operands");
+  // measured on B200 (round 2): a kind::f16 MMA whose A and B formats differ raises an illegal-instruction fault, although
+  // the instruction descriptor encodes them separately — so the library refuses mixed products up front
+  B200ST_CHECK(g.A.dtype == g.B.dtype, "tcgen05 kind::f16 needs A and B in the same 16-bit format (both bf16 or both fp16)");
   B200ST_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "empty GEMM");
   if (g_num_sms == 0) {
     int dev = 0;
