@@ -120,6 +120,46 @@ int b200st_forward(b200st_handle h, const b200st_buffers* buf, const b200st_batc
 /* forward + label-smoothed CE + full backward (GradAccumKerasModel.train_step, gradaccum_keras_model.py:190-245) */
 int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream);
 
+/* ---- inference: encoder pass, cached decoder step, greedy search (BASELINE cfg-5) ---------------------
+ * b200st_encode: modality + TransformerEncoder only (EncoderDecoderModel.get_symbols_to_logits_fn up to
+ * create_decoding_internal_cache, neurst/models/encoder_decoder_model.py:230-241): enc_out fp32 [B,T',d], enc_bias fp32
+ * [B,T'] = the additive memory bias (0 / -1e9).  Uses batch->src, src_length (speech) or src_ids, src_padding (text). */
+int b200st_encode(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, float* enc_out, float* enc_bias,
+                  void* stream);
+int64_t b200st_encode_workspace_bytes(b200st_handle h, int32_t B, int32_t T);
+/* Decoding state, caller-owned device buffers (nothing grows during decoding):
+ *   cross_kv  fp32 [dec_layers][B][Tm][2d]: memory keys | values, projected once (transformer_layers.py:156-170)
+ *   self_kv   fp32 [dec_layers][2][B][max_len][d]: self-attention key / value cache (multi_head_attention.py:271-289)
+ *   scratch   b200st_decode_scratch_floats(h, B) floats
+ * use_shadow 0: weights read from the fp32 master arena (token ids identical to an fp32 reference); 1: 16-bit shadow. */
+typedef struct {
+  int32_t B, Tm, max_len;
+  float* cross_kv; float* self_kv;
+  const float* memory_bias;
+  float* scratch;
+  int32_t use_shadow;
+} b200st_decode_state;
+int64_t b200st_decode_scratch_floats(b200st_handle h, int32_t B);
+/* TransformerDecoder.create_decoding_internal_cache + memorize_memory (transformer_decoder.py:105-147) */
+int b200st_decode_init(b200st_handle h, const b200st_buffers* buf, const float* enc_out, const b200st_decode_state* st, void* stream);
+/* symbols_to_logits_fn(symbols, cache, time) (encoder_decoder_model.py:243-253): symbols int64 [B] and the position *time_dev
+ * are device-resident; appends this position's keys/values to self_kv; logits fp32 [B,V]. */
+int b200st_decode_step(b200st_handle h, const b200st_buffers* buf, const b200st_decode_state* st, const int64_t* symbols,
+                       const int32_t* time_dev, float* logits, void* stream);
+/* sequence_beam_search with beam_size = 1 (neurst/layers/search/beam_search.py:254-439): log_softmax, finished rows emit EOS,
+ * UNK masked unless unk_id < 0, EOS masked before min_len, argmax (lowest index on ties), stop when every row has finished
+ * or after max_steps = min(T' + extra_decode_length, maximum_decode_length); out_ids [B,max_steps] is padded with EOS.
+ * The step is captured once into a CUDA graph and replayed (use_graph); `stream` must not be capturing. */
+typedef struct {
+  const int64_t* bos_ids;
+  int32_t eos_id, unk_id, min_len, max_steps;
+  int64_t* out_ids; int32_t* out_len; float* out_logprob;
+  void* state_words;            /* >= 128 bytes of device memory */
+  int32_t use_graph;
+} b200st_greedy_args;
+int b200st_greedy_search(b200st_handle h, const b200st_buffers* buf, const b200st_decode_state* st, const b200st_greedy_args* a,
+                         void* stream);
+
 /* 16-bit shadow of the parameter arena (tcgen05 operands); shadow_dtype = B200ST_BF16 or B200ST_F16 */
 int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtype, int64_t numel, void* stream);
 

@@ -165,6 +165,48 @@ int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b2
   if (batch->B <= 0 || batch->T <= 0 || batch->L <= 0) B200ST_FAIL("empty batch");
   return model_forward(h->m, to_buffers(buf), to_batch(batch), true, reinterpret_cast<cudaStream_t>(stream));
 }
+int b200st_encode(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, float* enc_out, float* enc_bias,
+                  void* stream) {
+  if (!h || !buf || !batch || !enc_out) B200ST_FAIL("null argument");
+  if (batch->B <= 0 || batch->T <= 0) B200ST_FAIL("empty batch");
+  Batch b = to_batch(batch);
+  b.L = 1; b.trg = nullptr; b.trg_length = nullptr; b.logits = nullptr;
+  b.enc_out = enc_out; b.stop_after_encoder = 1; b.enc_bias_out = enc_bias;
+  return model_forward(h->m, to_buffers(buf), b, false, reinterpret_cast<cudaStream_t>(stream));
+}
+int64_t b200st_encode_workspace_bytes(b200st_handle h, int32_t B, int32_t T) {
+  if (!h) return -1;
+  return (int64_t)model_workspace_bytes(h->m, B, T, 1, 0);
+}
+static DecodeState to_state(const b200st_decode_state* s) {
+  DecodeState d{};
+  d.B = s->B; d.Tm = s->Tm; d.max_len = s->max_len;
+  d.cross_kv = s->cross_kv; d.self_kv = s->self_kv; d.memory_bias = s->memory_bias; d.scratch = s->scratch;
+  d.use_shadow = s->use_shadow;
+  return d;
+}
+int64_t b200st_decode_scratch_floats(b200st_handle h, int32_t B) {
+  if (!h) return -1;
+  return decode_scratch_floats(h->m, B);
+}
+int b200st_decode_init(b200st_handle h, const b200st_buffers* buf, const float* enc_out, const b200st_decode_state* st, void* stream) {
+  if (!h || !buf || !st) B200ST_FAIL("null argument");
+  return decode_init(h->m, to_buffers(buf), enc_out, to_state(st), reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_decode_step(b200st_handle h, const b200st_buffers* buf, const b200st_decode_state* st, const int64_t* symbols,
+                       const int32_t* time_dev, float* logits, void* stream) {
+  if (!h || !buf || !st) B200ST_FAIL("null argument");
+  return decode_step(h->m, to_buffers(buf), to_state(st), symbols, time_dev, logits, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_greedy_search(b200st_handle h, const b200st_buffers* buf, const b200st_decode_state* st, const b200st_greedy_args* a,
+                         void* stream) {
+  if (!h || !buf || !st || !a) B200ST_FAIL("null argument");
+  GreedyArgs g{};
+  g.bos_ids = a->bos_ids; g.eos_id = a->eos_id; g.unk_id = a->unk_id; g.min_len = a->min_len; g.max_steps = a->max_steps;
+  g.out_ids = a->out_ids; g.out_len = a->out_len; g.out_logprob = a->out_logprob; g.state_words = a->state_words;
+  g.use_graph = a->use_graph;
+  return greedy_search(h->m, to_buffers(buf), to_state(st), g, reinterpret_cast<cudaStream_t>(stream));
+}
 int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtype, int64_t numel, void* stream) {
   if (!params || !shadow) B200ST_FAIL("null argument");
   return cast_f32_to_16(params, shadow, shadow_dtype, numel, reinterpret_cast<cudaStream_t>(stream));

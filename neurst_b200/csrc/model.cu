@@ -887,6 +887,11 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   }
   EncoderSave es;
   B200ST_TRY(encoder_fwd(c, x0, enc_bias, B, Ts, sc, es, b.enc_out));
+  if (b.stop_after_encoder) {
+    if (b.enc_bias_out)
+      RUN(cudaMemcpyAsync(b.enc_bias_out, enc_bias, sizeof(float) * (size_t)B * Ts, cudaMemcpyDeviceToDevice, c.st) == cudaSuccess ? 0 : 1);
+    return 0;
+  }
 
   // ---- decoder side ----
   float* y0 = c.f32((int64_t)Md * d);

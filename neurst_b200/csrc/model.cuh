@@ -78,6 +78,9 @@ struct Batch {
   float* nll_sum;                      // [B]
   float* n_tokens;                     // [B]
   float* enc_out;                      // fp32 [B,T',d]
+  // b200st_encode: stop after the encoder stack; enc_bias_out receives the additive key bias [B,T'] (0 / -1e9)
+  int stop_after_encoder = 0;
+  float* enc_bias_out = nullptr;
 };
 
 size_t model_workspace_bytes(const Model& m, int B, int T, int L, int training);
@@ -93,5 +96,30 @@ int mha_forward_api(const Model& m, const Buffers& buf, const float* query, cons
                     int Tk, float* out, cudaStream_t st, size_t* need);
 
 uint64_t dropout_stream_id(const std::string& site);
+
+// ---- incremental decoding (decode.cu) ----------------------------------------------------------------------------
+struct DecodeState {
+  int B, Tm, max_len;            // rows, encoder length T', cache length (maximum number of decoded positions)
+  float* cross_kv;               // [dec_layers][B][Tm][2d] fp32: pre-projected memory keys | values
+  float* self_kv;                // [dec_layers][2][B][max_len][d] fp32
+  const float* memory_bias;      // [B, Tm] additive (0 / -1e9) or null
+  float* scratch;                // decode_scratch_floats(B) floats
+  int use_shadow;                // 0: fp32 master weights, 1: the handle's 16-bit shadow
+};
+struct GreedyArgs {
+  const int64_t* bos_ids;        // [B] device: first decoder input (generation_initializer["decoder_input"])
+  int eos_id, unk_id;            // unk_id < 0: UNK allowed
+  int min_len, max_steps;
+  int64_t* out_ids;              // [B, max_steps] device, padded with EOS
+  int32_t* out_len;              // [B] device
+  float* out_logprob;            // [B] device: accumulated log-probability of the hypothesis
+  void* state_words;             // >= 128 bytes of device memory (ids, finished flags, time)
+  int use_graph;
+};
+int64_t decode_scratch_floats(const Model& m, int B);
+int decode_init(const Model& m, const Buffers& buf, const float* enc_out, const DecodeState& st, cudaStream_t s);
+int decode_step(const Model& m, const Buffers& buf, const DecodeState& st, const int64_t* symbols, const int32_t* time_dev,
+                float* logits, cudaStream_t s);
+int greedy_search(const Model& m, const Buffers& buf, const DecodeState& st, const GreedyArgs& ga, cudaStream_t s);
 
 }  // namespace b200st

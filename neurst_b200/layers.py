@@ -272,5 +272,5 @@ class TransformerDecoder(_B200Layer):
         """Incremental inference step with the concat self-attention cache (transformer_decoder.py:167-221).
         Composed from library launches (GEMM / LayerNorm / softmax); the per-layer cache tensors keep the
         reference's [B, i, H, dh] layout."""
-        from neurst_b200 import decode
-        return decode.decoder_step(self._rt, x, cache)
+        from neurst_b200 import layer_step
+        return layer_step.decoder_step(self._rt, x, cache)

@@ -162,6 +162,55 @@ class _EncoderDecoder:
 
     __call__ = forward
 
+    def get_symbols_to_logits_fn(self, inputs, is_training, is_inference, decode_padded_length=None):
+        """EncoderDecoderModel.get_symbols_to_logits_fn (neurst/models/encoder_decoder_model.py:211-261) ->
+        (symbols_to_logits_fn(symbols, cache, time=None), generation_initializer).
+
+        Training / teacher forcing (`is_inference=False`): the cache holds the inputs, `fn(trg_input [B,L], cache)` is the
+        fused full forward (logits [B,L,V]).  Inference: the encoder runs once (b200st_encode), the cache is a
+        `decode.DecodingCache` (pre-projected memory + preallocated self-attention K/V of `decode_padded_length` or
+        `maximum_decode_length` positions), `fn(symbols [B], cache, time)` is one b200st_decode_step (logits [B,V])."""
+        from neurst_b200 import decode as D
+        trg_meta = self._trg_meta
+        if not is_inference:
+            held = dict(inputs)
+
+            def symbols_to_logits_fn(symbols, cache, time=None):
+                b = dict(cache["inputs"])
+                b["trg_input"] = symbols
+                return self.forward(b, is_training=is_training)
+
+            init = {"decoder_input": inputs["trg_input"], "decoder_internal_cache": {"inputs": held, "decoding_states": None},
+                    "encoder_inputs_maxlen": None, "eos_id": trg_meta["eos_id"], "unk_id": trg_meta.get("unk_id")}
+            return symbols_to_logits_fn, init
+        if is_training:
+            raise NotImplementedError("dropout inside the incremental decoding loop is not supported")
+        rt = self._rt
+        enc, bias = D.encode(rt, inputs)
+        max_len = int(decode_padded_length or self._args.get("maximum_decode_length", 256))
+        cache = D.create_decoding_cache(rt, enc, bias, max_len, use_shadow=bool(self._args.get("decode_with_shadow", False)))
+
+        def symbols_to_logits_fn(symbols, cache, time=None):
+            return D.decoder_step_logits(rt, symbols, cache, 0 if time is None else int(time))
+
+        init = {"decoder_input": inputs["trg_input"], "decoder_internal_cache": cache, "encoder_inputs_maxlen": enc.shape[1],
+                "eos_id": trg_meta["eos_id"], "unk_id": trg_meta.get("unk_id")}
+        return symbols_to_logits_fn, init
+
+    def greedy_search(self, inputs, maximum_decode_length=256, extra_decode_length=50, minimum_decode_length=0, enable_unk=False,
+                      use_shadow=False):
+        """SequenceGenerator with search_method BeamSearch(beam_size=1) (neurst/exps/sequence_generator.py:62-86,
+        neurst/layers/search/beam_search.py:254-439) on the device: -> (token ids [B, maximum_decode_length], log-probs [B])."""
+        from neurst_b200 import decode as D
+        tm = self._trg_meta
+        B = inputs["src"].shape[0]
+        bos = inputs.get("trg_input")
+        if bos is None:
+            bos = torch.full((B,), int(tm["bos_id"]), dtype=torch.long)
+        ids, logprob, _ = D.greedy_search(self._rt, inputs, bos, tm["eos_id"], tm.get("unk_id"), maximum_decode_length,
+                                          extra_decode_length, minimum_decode_length, enable_unk, use_shadow)
+        return ids, logprob
+
     def evaluate(self, inputs, is_training=False):
         """logits + criterion outputs (nll_sum [B], n_tokens [B], loss) in one call."""
         return self._rt.run(self._batch(inputs, is_training, want_logits=True), backward=False)
@@ -173,6 +222,12 @@ class _EncoderDecoder:
 
 class SpeechTransformer(_EncoderDecoder):
     """ Defines the Speech Transformer model. """
+
+    @staticmethod
+    def class_or_method_args():
+        """Flag table of neurst_pt/models/speech_transformer.py:35-106 as (name, type, default, help) tuples; the registry
+        plug-in (neurst_b200/plugin.py) turns them into the reference's `Flag` objects."""
+        return _model_flags(True)
 
     @classmethod
     def build_model_args_by_name(cls, name):
@@ -194,6 +249,14 @@ class SpeechTransformer(_EncoderDecoder):
 
 class Transformer(_EncoderDecoder):
     """ Text Transformer (reference cfg-1 plumbing model). """
+
+    @staticmethod
+    def class_or_method_args():
+        return _model_flags(False)
+
+    @classmethod
+    def build_model_args_by_name(cls, name):
+        return None
 
     @classmethod
     def new(cls, args, src_meta, trg_meta, name=None, precision="fp32", label_smoothing=0.0, device="cuda"):

@@ -21,6 +21,7 @@ i.e. to the C ABI.  No tensor math lives here.
 import importlib
 
 _REGISTERED = {}
+_CLASSES = {}      # (backend, registry, class name) -> the registered class (created once per process)
 
 
 def reference_available():
@@ -37,7 +38,7 @@ def _ref_flags(table):
     return [Flag(name, dtype=ty, default=dflt, help=hlp) for name, ty, dflt, hlp in table]
 
 
-def _make_model_class(base, impl_cls, cls_name, speech):
+def _make_model_class(base, cls_name, impl_cls, speech):
     from neurst_b200 import models as M
 
     class _B200Model(base):
@@ -85,7 +86,7 @@ def _make_model_class(base, impl_cls, cls_name, speech):
     return _B200Model
 
 
-def _make_layer_class(base, impl_cls, cls_name):
+def _make_layer_class(base, cls_name, impl_cls):
     class _B200Layer(base):
         """ libb200st-backed drop-in for the reference layer of the same name (constructor signature unchanged). """
         IMPL = impl_cls
@@ -126,8 +127,12 @@ def register(override=False):
 
     out = {}
 
-    def put(backend, reg_name, register_fn, cls, aliases, stock):
-        register_fn(aliases)(cls)
+    def put(backend, reg_name, register_fn, make_cls, aliases, stock):
+        key = (backend, reg_name, make_cls[2])
+        if key not in _CLASSES:
+            _CLASSES[key] = make_cls[0](*make_cls[1:])
+            register_fn(aliases)(_CLASSES[key])
+        cls = _CLASSES[key]
         names = sorted(REG.REGISTRIED_CLS2ALIAS[backend][reg_name][cls.__name__])
         if override:
             for n in stock:
@@ -144,17 +149,17 @@ def register(override=False):
     from neurst_pt.layers.encoders.encoder import Encoder as PtEncoder
     from neurst_pt.layers.decoders.decoder import Decoder as PtDecoder
 
-    put("pt", "model", pt_register_model, _make_model_class(PtBaseModel, M.SpeechTransformer, "B200SpeechTransformer", True),
+    put("pt", "model", pt_register_model, (_make_model_class, PtBaseModel, "B200SpeechTransformer", M.SpeechTransformer, True),
         ["B200ST", "b200_speech_transformer"], ["SpeechTransformer", "speechtransformer", "speech_transformer"])
-    put("pt", "model", pt_register_model, _make_model_class(PtBaseModel, M.Transformer, "B200Transformer", False),
+    put("pt", "model", pt_register_model, (_make_model_class, PtBaseModel, "B200Transformer", M.Transformer, False),
         ["b200_transformer"], ["Transformer", "transformer"])
-    put("pt", "encoder", pt_register_encoder, _make_layer_class(PtEncoder, Ly.TransformerEncoder, "B200TransformerEncoder"),
+    put("pt", "encoder", pt_register_encoder, (_make_layer_class, PtEncoder, "B200TransformerEncoder", Ly.TransformerEncoder),
         ["b200_transformer_encoder"], ["TransformerEncoder", "transformerencoder", "transformer_encoder"])
-    put("pt", "decoder", pt_register_decoder, _make_layer_class(PtDecoder, Ly.TransformerDecoder, "B200TransformerDecoder"),
+    put("pt", "decoder", pt_register_decoder, (_make_layer_class, PtDecoder, "B200TransformerDecoder", Ly.TransformerDecoder),
         ["b200_transformer_decoder"], ["TransformerDecoder", "transformerdecoder", "transformer_decoder"])
-    put("pt", "base_layer", pt_register_layer, _make_layer_class(nn.Module, Ly.MultiHeadAttention, "B200MultiHeadAttention"),
+    put("pt", "base_layer", pt_register_layer, (_make_layer_class, nn.Module, "B200MultiHeadAttention", Ly.MultiHeadAttention),
         ["b200_multi_head_attention"], ["MultiHeadAttention", "multiheadattention", "multi_head_attention"])
-    put("pt", "base_layer", pt_register_layer, _make_layer_class(nn.Module, Ly.MultiHeadSelfAttention, "B200MultiHeadSelfAttention"),
+    put("pt", "base_layer", pt_register_layer, (_make_layer_class, nn.Module, "B200MultiHeadSelfAttention", Ly.MultiHeadSelfAttention),
         ["b200_multi_head_self_attention"],
         ["MultiHeadSelfAttention", "multiheadselfattention", "multi_head_self_attention"])
 
@@ -165,9 +170,10 @@ def register(override=False):
             raise ImportError("not a real TensorFlow")
         from neurst.models import register_model as tf_register_model
         from neurst.models.model import BaseModel as TfBaseModel
-        put("tf", "model", tf_register_model, _make_model_class(TfBaseModel, M.SpeechTransformer, "B200SpeechTransformer", True),
+        put("tf", "model", tf_register_model, (_make_model_class, TfBaseModel, "B200SpeechTransformer", M.SpeechTransformer, True),
             ["B200ST", "b200_speech_transformer"], ["SpeechTransformer", "speechtransformer", "speech_transformer"])
     except Exception:
         pass
+    _REGISTERED.clear()
     _REGISTERED.update(out)
     return out

@@ -44,8 +44,9 @@ class Runtime:
         self.lib = L.load()
         self.config = config
         self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise L.B200STError("neurst_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise L.B200STError("neurst_b200 runs on CUDA devices only (no CPU fallback): device=%s, CUDA available=%s" %
+                                (self.device, torch.cuda.is_available()))
         h = C.c_void_p()
         L.check(self.lib.b200st_create(C.byref(config), C.byref(h)))
         self.handle = h

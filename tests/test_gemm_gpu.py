@@ -22,7 +22,7 @@ def _ref(A, B, a_mn, b_mn):
 @pytest.mark.parametrize("cdt", ["f32", "bf16", "f16"])
 def test_operand_formats(adt, bdt, a_mn, b_mn, cdt):
     g = torch.Generator(device="cuda").manual_seed(1)
-    M, N, K = 300, 192, 136
+    M, N, K = 304, 192, 136          # ragged tiles; MN-major rows must be 16-byte multiples for TMA (M % 8 == 0)
     A = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g).to(DT[adt])
     B = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g).to(DT[bdt])
     C = torch.zeros(M, N, device="cuda", dtype=DT[cdt])

@@ -36,7 +36,7 @@ def test_forward_bf16_vs_reference_fixture():
     assert err < 5e-2, err
 
 
-@pytest.mark.parametrize("precision,tol_logits,tol_grad", [("fp32", 1e-4, 2e-4), ("fp16", 8e-3, 2e-2), ("bf16", 6e-2, 1e-1)])
+@pytest.mark.parametrize("precision,tol_logits,tol_grad", [("fp32", 1e-4, 2e-4), ("fp16", 8e-3, 5e-2), ("bf16", 6e-2, 1e-1)])
 @pytest.mark.parametrize("dropout", [0.0, 0.1])
 @pytest.mark.parametrize("channels", [64, 256])      # 256 = the production front-end kernels (normalised-save conv1 path)
 def test_forward_backward_vs_oracle(precision, tol_logits, tol_grad, dropout, channels):
