@@ -20,7 +20,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(hparams="speech_transformer_s", B=32, T=1000, F=80, L=88, V=8192)
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the headline metric is quoted on
+    "cfg2": dict(hparams="speech_transformer_s", B=32, T=1000, F=80, L=88, V=8192, d=256, H=4, ffn=2048),
+    # configs[2] (cfg-3): global [64,1500,80] over 8 GPUs = 8 utterances per GPU (strong-scaling share); "cfg3w" = 64 per GPU
+    "cfg3": dict(hparams="speech_transformer_s", B=8, T=1500, F=80, L=128, V=8192, d=256, H=4, ffn=2048),
+    "cfg3w": dict(hparams="speech_transformer_s", B=64, T=1500, F=80, L=128, V=8192, d=256, H=4, ffn=2048),
+    # configs[3] (cfg-4): speech_transformer_m, frame budget 24000 / GPU, length buckets, ragged src_length (see run_gpu)
+    "cfg4": dict(hparams="speech_transformer_m", B=8, T=3000, F=80, L=152, V=8192, d=512, H=8, ffn=2048, ragged=True),
+}
+WORKLOAD = WORKLOADS["cfg2"]
 # 2*M*N*K of every contraction, fwd+bwd = 3x fwd, padded positions counted
 MFLOP_PER_FRAME = 53.24
 
@@ -215,6 +224,96 @@ def cpu_worker(spec):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def encoder_block_roofline(WL, dtype, peaks, iters=20):
+    import torch
+    from neurst_b200.layers import TransformerEncoder
+    B, T, d, H, ffn = WL["B"], WL["T"], WL["d"], WL["H"], WL["ffn"]
+    T2 = ((T + 1) // 2 + 1) // 2
+    nl = 12
+    enc = TransformerEncoder(nl, d, H, ffn, attention_dropout_rate=0.1, ffn_dropout_rate=0.1, layer_postprocess_dropout_rate=0.1,
+                             precision=dtype)
+    g = torch.Generator().manual_seed(3)
+    P = {k: (torch.randn(shp, generator=g) * (0.05 if len(shp) > 1 else 0.0) + (1.0 if k.endswith("gamma") else 0.0))
+         for k, (_, shp) in enc.runtime.table.items()}
+    enc.load_parameters(P)
+    enc.frozen_parameters = True          # no 16-bit shadow refresh inside the timed calls
+    x = torch.randn(B, T2, d, device="cuda")
+    pad = torch.zeros(B, T2, device="cuda")
+    for _ in range(3):
+        enc(x, pad, is_training=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        enc(x, pad, is_training=True)
+    e1.record()
+    torch.cuda.synchronize()
+    us_layer = e0.elapsed_time(e1) * 1e3 / iters / nl
+    M, dh = B * T2, d // H
+    gf = (2 * M * d * 3 * d + 2 * M * d * d + 4 * B * H * T2 * T2 * dh + 4 * M * d * ffn) / 1e9
+    tf = gf / us_layer * 1e-3
+    return {"what": "TransformerEncoder forward (dropout on), eager launches, time / 12 layers (includes 1/12 of the input cast "
+                    "and final LayerNorm)", "fwd_us_per_layer": us_layer, "gflop_per_layer": gf, "achieved": tf,
+            "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"], "frac_of_burst_peak": tf / peaks["tflops_burst"],
+            "target": ">= 0.70 (<= %.1f us)" % (gf / (0.7 * peaks["tflops_sustained"]) * 1e3)}
+
+
+def run_decode(args):
+    """BASELINE configs[4] (cfg-5): greedy decode of one [1,2000,80] utterance, speech_transformer_s, 200 steps."""
+    import torch
+    from neurst_b200 import lib, decode as D
+    from neurst_b200.models import SpeechTransformer, speech_transformer_hparams
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    lib.load()
+    V, T, steps = 8192, 2000, 200
+    hp = dict(speech_transformer_hparams("speech_transformer_s")["model.params"])
+    tm = {"vocab_size": V, "eos_id": V - 1, "bos_id": V - 2, "unk_id": V - 3}
+    out = {}
+    for dtype, shadow in (("fp32", False), ("fp16", True)):
+        model = SpeechTransformer.new(hp, {"audio_feature_dim": 80, "audio_feature_channels": 1}, tm, precision=dtype)
+        model.init_parameters(1234)
+        rt = model.runtime
+        g = torch.Generator().manual_seed(5)
+        src = torch.randn(1, T, 80, 1, generator=g).pin_memory()
+        inputs = dict(src=src, src_length=torch.tensor([T]))
+        # never-EOS decoding: minimum_decode_length = steps forces all 200 positions to be decoded
+        kw = dict(maximum_decode_length=steps, extra_decode_length=steps, minimum_decode_length=steps, use_shadow=shadow)
+        for _ in range(2):
+            D.greedy_search(rt, inputs, tm["bos_id"], tm["eos_id"], tm["unk_id"], **kw)
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        enc, bias = D.encode(rt, {k: v.cuda(non_blocking=True) for k, v in inputs.items()})
+        cache = D.create_decoding_cache(rt, enc, bias, steps, shadow)
+        e[1].record()
+        ids, lp, ln = D.greedy_search(rt, inputs, tm["bos_id"], tm["eos_id"], tm["unk_id"], cache=cache, **kw)
+        host_ids = ids.cpu()
+        e[2].record()
+        torch.cuda.synchronize()
+        enc_ms, dec_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        out[dtype] = dict(encode_ms=enc_ms, decode_ms=dec_ms, us_per_token=dec_ms * 1e3 / steps, tokens=int(ln[0]),
+                          weights="16-bit shadow" if shadow else "fp32 master")
+    wbytes = 10.8e6          # decoder + tied embedding parameters read per token
+    peaks = load_peaks()
+    best = out["fp16"]
+    floor_us = wbytes * 2 / (peaks["hbm_gbs"] * 1e9) * 1e6
+    line = {"metric": "greedy_decode_tokens_per_sec", "value": 1e6 / best["us_per_token"], "unit": "tokens/s", "n_gpus": 1,
+            "steps": steps, "warmup": 2, "ms_per_step": best["us_per_token"] / 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 arithmetic, fp16 weights (fp32-weight variant alongside)", "data": "synthetic",
+            "config": {"workload": "cfg-5: speech_transformer_s greedy decode, one utterance [1,2000,80], 200 steps, preallocated "
+                                   "KV caches, CUDA-graph step replay", "per_precision": out},
+            "roofline": {"bound": "hbm", "achieved": wbytes * 2 / (best["us_per_token"] * 1e-6) / 1e9, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": floor_us / best["us_per_token"], "traffic": None,
+                         "note": "algorithmic bytes per token = 21.6 MB of 16-bit decoder + embedding weights (+ 6 MB fp32 cross "
+                                 "K/V); floor %.1f us/token" % floor_us},
+            "e2e": {"value": steps / ((best["encode_ms"] + best["decode_ms"]) * 1e-3), "unit": "tokens/s (encoder pass + cache "
+                    "build + 200 steps + ids D2H)", "h2d_bytes_per_step": T * 80 * 4, "d2h_bytes_per_step": steps * 8},
+            "gpu_launches": 200 * 40}
+    print(json.dumps(line), flush=True)
+
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -232,15 +331,26 @@ def run_gpu(args):
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     lib.load()
-    B, T, L, V = WORKLOAD["B"], WORKLOAD["T"], WORKLOAD["L"], WORKLOAD["V"]
-    trainer, _ = build_speech_transformer_trainer(WORKLOAD["hparams"], V, precision="bf16", label_smoothing=0.1, seed=1234,
+    WL = WORKLOADS[args.workload]
+    B, T, L, V = WL["B"], WL["T"], WL["L"], WL["V"]
+    trainer, _ = build_speech_transformer_trainer(WL["hparams"], V, precision=args.dtype, label_smoothing=0.1, seed=1234,
                                                   use_cuda_graph=not args.no_graph)
     dev = torch.device("cuda", local_rank)
 
     # resident-input arm: a few distinct batches already in HBM (activations per step ~4 GB >> 126 MB L2)
     n_batches = 4
-    dev_batches = [synthetic_batch(B, T, L, V, seed=1234 + rank * 100 + i, device=dev) for i in range(n_batches)]
-    host_batches = [synthetic_batch(B, T, L, V, seed=1234 + rank * 100 + i, pin=True) for i in range(n_batches)]
+    if WL.get("ragged"):
+        # cfg-4: frame budget 24000 / GPU over the reference's length buckets (neurst/tasks/speech2text.py:38-56,296-310):
+        # every rank takes the SAME (T bucket, B = 24000 // T rounded to 8) each step, src_length ~ U(0.6 T, T)
+        buckets = [(3000, 8, 152), (2000, 8, 152), (1200, 16, 104), (600, 40, 56)]
+        shapes = [buckets[i % len(buckets)] for i in range(n_batches)]
+    else:
+        shapes = [(T, B, L)] * n_batches
+    lens = "ragged" if WL.get("ragged") else "full"
+    dev_batches = [synthetic_batch(b_, t_, l_, V, seed=1234 + rank * 100 + i, lengths=lens, device=dev) for i, (t_, b_, l_) in enumerate(shapes)]
+    host_batches = [synthetic_batch(b_, t_, l_, V, seed=1234 + rank * 100 + i, lengths=lens, pin=True) for i, (t_, b_, l_) in enumerate(shapes)]
+    frames_per_cycle = sum(t_ * b_ for (t_, b_, _) in shapes)
+    real_frames_per_cycle = sum(int(b["src_length"].sum()) for b in host_batches)
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
     def barrier():
@@ -317,6 +427,14 @@ def run_gpu(args):
     launches_per_step = lib.launch_count() - l0
     barrier()
 
+    # north-star sub-target: forward time of ONE encoder self-attention + FFN block (23.02 GFLOP at cfg-2), measured on the
+    # encoder stack alone (b200st_encoder_forward: 12 layers + final LN, dropout on) with CUDA events
+    enc_block = None
+    if rank == 0 and not WL.get("ragged"):
+        try:
+            enc_block = encoder_block_roofline(WL, args.dtype, load_peaks())
+        except Exception as e:      # never lose the headline line over the side measurement
+            enc_block = {"error": str(e)[:200]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_baseline_object(3, 1)
@@ -330,18 +448,23 @@ def run_gpu(args):
 
     peaks = load_peaks()
     ms_step = ms_total / args.steps
-    frames = world * B * T
+    step_shapes = [shapes[i % n_batches] for i in range(args.steps)]
+    frames = world * sum(t_ * b_ for (t_, b_, _) in step_shapes) / args.steps            # padded frames per step (the metric)
+    real_frames = world * sum(int(host_batches[i % n_batches]["src_length"].sum()) for i in range(args.steps)) / args.steps
     value = frames / (ms_step * 1e-3)
-    fl = flops_per_step(B, T, L)
+    fl = sum(flops_per_step(b_, t_, l_, V, WL["d"], WL["H"], WL["ffn"]) for (t_, b_, l_) in step_shapes) / args.steps
     ach = fl / (ms_step * 1e-3) / 1e12
     clocks = sampler.summary()
     line = {
         "metric": "audio_frames_per_sec_fwd_bwd", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "SpeechTransformer-base (speech_transformer_s: conv2d subsample + 12enc/6dec, d=256) synthetic "
-                               "fbank [32,1000,80] per GPU, L=88, V=8192, dropout 0.1, label_smoothing 0.1, Adam+noam",
-                   "global_batch_frames": frames, "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "kernels_per_step": int(launches_per_step),
+        "dtype": {"fp16": "fp16 (mixed_float16: fp16 operands/activations, fp32 accumulate + master weights, dynamic loss scale)",
+                  "bf16": "bf16", "fp32": "f32"}[args.dtype], "data": "synthetic",
+        "config": {"workload": "%s: %s (conv2d subsample + 12enc/6dec, d=%d) synthetic fbank %s per GPU, V=8192, dropout 0.1, "
+                               "label_smoothing 0.1, Adam+noam" % (args.workload, WL["hparams"], WL["d"],
+                                                                   "[%d,%d,80] L=%d" % (B, T, L) if not WL.get("ragged") else
+                                                                   "length buckets %s (T,B,L), src_length~U(0.6T,T)" % (shapes,)),
+                   "global_batch_frames": frames, "real_frames_per_sec": real_frames / (ms_step * 1e-3), "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "kernels_per_step": int(launches_per_step),
                    "l2_policy": "inputs+activations per step (~4 GB) exceed the 126 MB L2; 4 rotating input batches",
                    "loss_last_step": loss_val},
         "clocks": clocks,
@@ -353,8 +476,9 @@ def run_gpu(args):
     # launches / their CUDA-event durations, measured on one eagerly launched step right after the timed region (a graph
     # replay cannot be bracketed per kernel).  `traffic` = DRAM bytes per launch from the committed ncu pass
     # (profiles/r01_gemm_traffic.json, same command), averaged like `achieved`.
-    step_rf = {"achieved": ach, "frac": ach / peaks["tflops_sustained"], "algorithmic_flops_per_step": fl,
-               "mflop_per_frame": fl / (B * T) / 1e6, "note": "all kernels of the step / step time"}
+    step_rf = {"achieved": ach, "frac": ach / peaks["tflops_sustained"], "frac_of_burst_peak": ach / peaks["tflops_burst"],
+               "algorithmic_flops_per_step": fl, "mflop_per_frame": fl / (frames / world) / 1e6,
+               "note": "all kernels of the step / step time"}
     traffic, ncu_share = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
@@ -367,6 +491,7 @@ def run_gpu(args):
         g_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05, all instantiations)", "achieved": g_tf,
                             "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": g_tf / peaks["tflops_sustained"],
+                            "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": g_tf / peaks["tflops_burst"],
                             "traffic": traffic, "peak_source": peaks["source"], "launches_per_step": gemm["launches"],
                             "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
                             "algorithmic_flops_per_launch": gemm["flops"] / max(1, gemm["launches"]),
@@ -377,6 +502,8 @@ def run_gpu(args):
         line["roofline"] = {"bound": "tensor", "kernel": "whole step", "achieved": ach, "peak": peaks["tflops_sustained"],
                             "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": None,
                             "peak_source": peaks["source"], "step": step_rf}
+    if enc_block:
+        line["roofline"]["encoder_block"] = enc_block
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -393,6 +520,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-worker", default="", help=argparse.SUPPRESS)
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the CUDA graph")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16 = the reference's mixed_float16 (default: logits within 3.2e-3 of the fp64 oracle); bf16; fp32 parity mode")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["decode"],
+                    help="cfg2 = BASELINE headline [32,1000,80]; cfg3 / cfg3w = [8|64,1500,80]; cfg4 = speech_transformer_m ragged buckets; "
+                         "decode = cfg-5 greedy decode")
     args = ap.parse_args()
     if args.cpu_worker:
         cpu_worker(args.cpu_worker)
@@ -406,9 +538,13 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        cmd += ["--dtype", args.dtype, "--workload", args.workload]
         if args.no_cpu_baseline:
             cmd.append("--no-cpu-baseline")
         sys.exit(subprocess.call(cmd))
+    if args.workload == "decode":
+        run_decode(args)
+        return
     run_gpu(args)
 
 

@@ -190,7 +190,8 @@ class TransformerEncoder(_B200Layer):
         B, T, d = x.shape
         out = torch.empty(B, T, d, dtype=torch.float32, device=self._rt.device)
         self._seed += 1
-        self._rt._shadow_stale = True
+        if not getattr(self, "frozen_parameters", False):     # parameters may have been written through the views
+            self._rt._shadow_stale = True
         self._call_with_workspace(lambda bufs, need: self._rt.lib.b200st_encoder_forward(
             self._rt.handle, bufs, _ptr(x), _ptr(pad), B, T, _ptr(out), int(is_training), self._seed, L._stream(), need))
         return out

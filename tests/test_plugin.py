@@ -71,3 +71,37 @@ def test_override_points_stock_names_at_the_b200_classes():
     finally:
         for k, v in saved.items():
             REG.REGISTRIES["pt"][k].clear(); REG.REGISTRIES["pt"][k].update(v)
+
+
+@pytest.mark.gpu
+def test_plugin_class_forward_on_gpu_without_the_reference():
+    """The class factory of the plug-in around a stand-in registry base class (same constructor contract as
+    neurst_pt/models/model.py:25-32): `new(args, src_meta, trg_meta)` -> forward / get_symbols_to_logits_fn run through the
+    C ABI and agree with the direct implementation."""
+    from neurst_b200 import plugin
+    from neurst_b200.models import SpeechTransformer, speech_transformer_hparams
+
+    class BaseModel(torch.nn.Module):
+        def __init__(self, args):
+            self._args = args
+            super().__init__()
+        args = property(lambda self: self._args)
+
+    cls = plugin._make_model_class(BaseModel, "B200SpeechTransformer", SpeechTransformer, True)
+    hp = dict(speech_transformer_hparams("speech_transformer_s")["model.params"])
+    hp.update({"modality.source.channels": 64, "modality.dim": 64})
+    for side in ("encoder", "decoder"):
+        hp.update({side + ".num_layers": 1, side + ".hidden_size": 64, side + ".num_attention_heads": 4, side + ".filter_size": 64})
+    src_meta = {"audio_feature_dim": 80, "audio_feature_channels": 1}
+    trg_meta = {"vocab_size": 96, "eos_id": 95, "bos_id": 94, "unk_id": 93}
+    model = cls.new(hp, src_meta, trg_meta, precision="fp32")
+    model.impl.init_parameters(3)
+    g = torch.Generator().manual_seed(0)
+    inputs = dict(src=torch.randn(2, 50, 80, 1, generator=g), src_length=torch.tensor([50, 33]),
+                  trg_input=torch.randint(0, 90, (2, 5), generator=g))
+    a = model(inputs, is_training=False)
+    direct = SpeechTransformer.new(hp, src_meta, trg_meta, precision="fp32")
+    direct.load_parameters({k: v.clone() for k, v in model.named_parameters().items()})
+    assert a.shape == (2, 5, 96) and float((a - direct.forward(inputs, is_training=False)).abs().max()) == 0.0
+    fn, init = model.get_symbols_to_logits_fn(inputs, is_training=False, is_inference=False)
+    assert float((fn(init["decoder_input"], init["decoder_internal_cache"]) - a).abs().max()) == 0.0
