@@ -159,6 +159,8 @@ typedef struct {
 } b200st_greedy_args;
 int b200st_greedy_search(b200st_handle h, const b200st_buffers* buf, const b200st_decode_state* st, const b200st_greedy_args* a,
                          void* stream);
+/* 1 when the last b200st_greedy_search replayed a captured graph, 0 when it launched eagerly (e.g. legacy default stream) */
+int32_t b200st_greedy_used_graph(void);
 
 /* 16-bit shadow of the parameter arena (tcgen05 operands); shadow_dtype = B200ST_BF16 or B200ST_F16 */
 int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtype, int64_t numel, void* stream);

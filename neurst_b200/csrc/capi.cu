@@ -207,6 +207,7 @@ int b200st_greedy_search(b200st_handle h, const b200st_buffers* buf, const b200s
   g.use_graph = a->use_graph;
   return greedy_search(h->m, to_buffers(buf), to_state(st), g, reinterpret_cast<cudaStream_t>(stream));
 }
+int32_t b200st_greedy_used_graph(void) { return last_greedy_used_graph(); }
 int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtype, int64_t numel, void* stream) {
   if (!params || !shadow) B200ST_FAIL("null argument");
   return cast_f32_to_16(params, shadow, shadow_dtype, numel, reinterpret_cast<cudaStream_t>(stream));

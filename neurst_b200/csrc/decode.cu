@@ -425,6 +425,9 @@ int raise_all_smem(const Config& cf, const DecodeState& st) {
 
 }  // namespace
 
+static int g_last_greedy_graph = -1;
+int last_greedy_used_graph() { return g_last_greedy_graph; }
+
 int64_t decode_scratch_floats(const Model& m, int B) { return layout_of(m.cfg, B).total + 64; }
 
 // memorize_memory (transformer_layers.py:156-160): K/V projections of the encoder output, once per utterance, fp32
@@ -503,6 +506,7 @@ int greedy_search(const Model& m, const Buffers& buf, const DecodeState& st, con
       cudaGetLastError();
     }
   }
+  g_last_greedy_graph = graphed ? 1 : 0;
   static thread_local int32_t* flag_host = nullptr;     // pinned word for the "all rows finished" poll
   if (!flag_host) B200ST_CUDA(cudaMallocHost(&flag_host, sizeof(int32_t)));
   *flag_host = 0;

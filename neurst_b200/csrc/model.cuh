@@ -120,6 +120,7 @@ int64_t decode_scratch_floats(const Model& m, int B);
 int decode_init(const Model& m, const Buffers& buf, const float* enc_out, const DecodeState& st, cudaStream_t s);
 int decode_step(const Model& m, const Buffers& buf, const DecodeState& st, const int64_t* symbols, const int32_t* time_dev,
                 float* logits, cudaStream_t s);
+int last_greedy_used_graph();      // 1 / 0 for the last greedy_search of this process (-1: none yet)
 int greedy_search(const Model& m, const Buffers& buf, const DecodeState& st, const GreedyArgs& ga, cudaStream_t s);
 
 }  // namespace b200st

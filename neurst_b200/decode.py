@@ -143,7 +143,17 @@ def greedy_search(rt, inputs, bos_id, eos_id, unk_id=None, maximum_decode_length
     a.out_ids, a.out_len, a.out_logprob = out.data_ptr(), length.data_ptr(), logprob.data_ptr()
     a.state_words, a.use_graph = words.data_ptr(), int(bool(use_graph))
     bufs = _bufs(rt)
-    L.check(rt.lib.b200st_greedy_search(rt.handle, C.byref(bufs), C.byref(cache.state), C.byref(a), L._stream()))
+    # the library captures the step into a CUDA graph: that needs a real (non-legacy-default) stream
+    cur = torch.cuda.current_stream(dev)
+    side = getattr(rt, "_decode_stream", None)
+    if side is None:
+        side = rt._decode_stream = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        L.check(rt.lib.b200st_greedy_search(rt.handle, C.byref(bufs), C.byref(cache.state), C.byref(a), L._stream()))
+    cur.wait_stream(side)
+    if use_graph and int(rt.lib.b200st_greedy_used_graph()) != 1:
+        raise L.B200STError("greedy search could not capture its step graph")
     if steps < maximum_decode_length:      # padded to the fixed output length with EOS (beam_search.py:428-436)
         out = torch.cat([out, torch.full((B, maximum_decode_length - steps), int(eos_id), dtype=torch.int64, device=dev)], 1)
     return out, logprob, length
