@@ -120,6 +120,27 @@ int b200st_forward(b200st_handle h, const b200st_buffers* buf, const b200st_batc
 /* forward + label-smoothed CE + full backward (GradAccumKerasModel.train_step, gradaccum_keras_model.py:190-245) */
 int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, void* stream);
 
+/* ---- data-parallel training step: NCCL over NVLink only, inside the library -----------------------------
+ * One process per GPU.  Rank 0 calls b200st_comm_unique_id, the 128 bytes travel to the other ranks by any host channel,
+ * every rank calls b200st_comm_init (ncclCommInitRank; libnccl.so.2 is dlopen'ed from the process or the system).
+ * b200st_train_step = forward + loss + backward (+ allreduce_grads: ncclAllReduce(sum) of the fp32 gradient arena in
+ * reverse-order buckets — decoder+output layer / upper encoder half / lower encoder half / front-end — each issued on the
+ * library's communication stream the moment its last gradient kernel has been enqueued, so the transfers run under the
+ * rest of the backward pass; `stream` waits for them at the end) (+ optim != NULL: b200st_optimizer_step with
+ * grad_scale = 1/(replicas * update_cycle) = hvd.Average, neurst/training/hvd_utils.py:48-62).
+ * b200st_comm_broadcast: rank-0 parameters to all (neurst/exps/trainer.py:285). */
+int b200st_comm_unique_id(char* out128);
+int b200st_comm_init(b200st_handle h, const char* id128, int32_t nranks, int32_t rank);
+int b200st_comm_broadcast(b200st_handle h, float* buf, int64_t numel, int32_t root, void* stream);
+int b200st_comm_stats(b200st_handle h, int64_t* reduced_elems, int32_t* calls, int32_t* world);   /* of the last step */
+struct b200st_optim_args_;
+typedef struct {
+  int32_t allreduce_grads;
+  const struct b200st_optim_args_* optim;     /* NULL: no optimizer step (gradient accumulation micro-step) */
+} b200st_step_opts;
+int b200st_train_step(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, const b200st_step_opts* opts,
+                      void* stream);
+
 /* ---- inference: encoder pass, cached decoder step, greedy search (BASELINE cfg-5) ---------------------
  * b200st_encode: modality + TransformerEncoder only (EncoderDecoderModel.get_symbols_to_logits_fn up to
  * create_decoding_internal_cache, neurst/models/encoder_decoder_model.py:230-241): enc_out fp32 [B,T',d], enc_bias fp32
@@ -172,7 +193,7 @@ int b200st_refresh_shadow(const float* params, void* shadow, int32_t shadow_dtyp
  * skipped steps, applied steps, global gradient norm, 1/scale latch, reserved}; a step whose gradients are not all finite
  * is skipped (parameters untouched, gradients zeroed) and halves the scale; `growth_steps` finite steps double it.
  * h may be NULL (whole arena = one tensor). tensor_sumsq: device float[param_count + 1] scratch (clip_norm / loss scale). */
-typedef struct {
+typedef struct b200st_optim_args_ {
   float* params; float* grads; float* m; float* v;
   void* shadow; int32_t shadow_dtype;
   int64_t numel;

@@ -121,7 +121,43 @@ int b200st_create(const b200st_config* cfg, b200st_handle* out) {
   *out = h;
   return 0;
 }
-int b200st_destroy(b200st_handle h) { delete h; return 0; }
+static Batch to_batch(const b200st_batch* b);
+static Buffers to_buffers(const b200st_buffers* b);
+int b200st_comm_unique_id(char* out128) {
+  if (!out128) B200ST_FAIL("null argument");
+  return comm_unique_id(out128);
+}
+int b200st_comm_init(b200st_handle h, const char* id128, int32_t nranks, int32_t rank) {
+  if (!h || !id128) B200ST_FAIL("null argument");
+  if (h->m.sync) { comm_destroy(h->m.sync); h->m.sync = nullptr; }
+  return comm_init(&h->m.sync, id128, nranks, rank);
+}
+int b200st_comm_stats(b200st_handle h, int64_t* reduced_elems, int32_t* calls, int32_t* world) {
+  if (!h) B200ST_FAIL("null handle");
+  if (reduced_elems) *reduced_elems = comm_reduced_elems(h->m.sync);
+  if (calls) *calls = comm_calls(h->m.sync);
+  if (world) *world = comm_world(h->m.sync);
+  return 0;
+}
+int b200st_comm_broadcast(b200st_handle h, float* buf, int64_t numel, int32_t root, void* stream) {
+  if (!h || !buf) B200ST_FAIL("null argument");
+  if (!h->m.sync) B200ST_FAIL("b200st_comm_init has not been called on this handle");
+  return comm_broadcast(h->m.sync, buf, numel, root, reinterpret_cast<cudaStream_t>(stream));
+}
+int b200st_train_step(b200st_handle h, const b200st_buffers* buf, const b200st_batch* batch, const b200st_step_opts* opts, void* stream) {
+  if (!h || !buf || !batch) B200ST_FAIL("null argument");
+  if (batch->B <= 0 || batch->T <= 0 || batch->L <= 0) B200ST_FAIL("empty batch");
+  Batch b = to_batch(batch);
+  b.allreduce_grads = (opts && opts->allreduce_grads) ? 1 : 0;
+  B200ST_TRY(model_forward(h->m, to_buffers(buf), b, true, reinterpret_cast<cudaStream_t>(stream)));
+  if (opts && opts->optim) return b200st_optimizer_step(h, opts->optim, stream);
+  return 0;
+}
+int b200st_destroy(b200st_handle h) {
+  if (h && h->m.sync) { comm_destroy(h->m.sync); h->m.sync = nullptr; }
+  delete h;
+  return 0;
+}
 int64_t b200st_param_arena_numel(b200st_handle h) { return h ? h->m.arena_numel : -1; }
 int32_t b200st_param_count(b200st_handle h) { return h ? (int32_t)h->m.params.size() : -1; }
 int b200st_param_info(b200st_handle h, int32_t i, char* name, int32_t name_cap, int64_t* offset, int32_t* ndim, int64_t* shape4) {

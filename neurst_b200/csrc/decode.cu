@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) gemv_kernel(const float* __restrict__ in,
 // cache at position `time` (multi_head_attention.py:271-276); else q from `qsrc`, keys = pre-projected memory with the
 // additive memory bias.  q is scaled by dh^-0.5 after the projection bias (multi_head_attention.py:203).
 template <typename TW, bool SELF>
-__global__ void __launch_bounds__(128) attn_step_kernel(const float* __restrict__ qsrc, int q_ld, float* __restrict__ kcache,
+__global__ void __launch_bounds__(256) attn_step_kernel(const float* __restrict__ qsrc, int q_ld, float* __restrict__ kcache,
                                                         float* __restrict__ vcache, int kv_ld, int cache_rows,
                                                         const float* __restrict__ mem_bias, const TW* __restrict__ Wo,
                                                         const float* __restrict__ bo, float* __restrict__ x, int d, int dh, int Tm,
@@ -165,13 +165,21 @@ __global__ void __launch_bounds__(128) attn_step_kernel(const float* __restrict_
     }
   }
   __syncthreads();
-  // scores: one warp per key (lanes across the head dim)
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int j = w; j < nk; j += 4) {
+  // scores: one thread per key — its dh-float key row is read with independent 16-byte loads (no cross-lane reduction,
+  // every load of the row in flight at once: the loop is latency-bound otherwise)
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+    const float* kr = kbase + (int64_t)j * kv_ld;
     float s = 0.f;
-    for (int c = lane; c < dh; c += 32) s = fmaf(q[c], kbase[(int64_t)j * kv_ld + c], s);
-    s = warp_sum(s);
-    if (lane == 0) sc[j] = s + ((!SELF && mem_bias) ? mem_bias[(int64_t)b * Tm + j] : 0.f);
+    if ((dh & 3) == 0) {
+#pragma unroll 4
+      for (int c = 0; c < dh; c += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(kr + c);
+        s = fmaf(q[c], kk.x, fmaf(q[c + 1], kk.y, fmaf(q[c + 2], kk.z, fmaf(q[c + 3], kk.w, s))));
+      }
+    } else {
+      for (int c = 0; c < dh; ++c) s = fmaf(q[c], kr[c], s);
+    }
+    sc[j] = s + ((!SELF && mem_bias) ? mem_bias[(int64_t)b * Tm + j] : 0.f);
   }
   __syncthreads();
   float mx = -INFINITY;
@@ -181,15 +189,22 @@ __global__ void __launch_bounds__(128) attn_step_kernel(const float* __restrict_
   for (int j = threadIdx.x; j < nk; j += blockDim.x) { const float e = expf(sc[j] - mx); sc[j] = e; se += e; }
   se = block_sum(se, red);
   const float inv = 1.f / se;
-  // ctx[c] = sum_j p_j V[j][c]: thread pairs (c, key parity)
+  // ctx[c] = sum_j p_j V[j][c]: thread = (column c, key partition); 4 independent partial sums per thread
   for (int c = threadIdx.x; c < dh; c += blockDim.x) ctx[c] = 0.f;
   __syncthreads();
   {
     const int c = threadIdx.x % dh, part = threadIdx.x / dh, nparts = blockDim.x / dh > 0 ? blockDim.x / dh : 1;
     if (part < nparts) {
-      float a = 0.f;
-      for (int j = part; j < nk; j += nparts) a = fmaf(sc[j], vbase[(int64_t)j * kv_ld + c], a);
-      atomicAdd(&ctx[c], a * inv);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int j = part;
+      for (; j + 3 * nparts < nk; j += 4 * nparts) {
+        a0 = fmaf(sc[j], vbase[(int64_t)j * kv_ld + c], a0);
+        a1 = fmaf(sc[j + nparts], vbase[(int64_t)(j + nparts) * kv_ld + c], a1);
+        a2 = fmaf(sc[j + 2 * nparts], vbase[(int64_t)(j + 2 * nparts) * kv_ld + c], a2);
+        a3 = fmaf(sc[j + 3 * nparts], vbase[(int64_t)(j + 3 * nparts) * kv_ld + c], a3);
+      }
+      for (; j < nk; j += nparts) a0 = fmaf(sc[j], vbase[(int64_t)j * kv_ld + c], a0);
+      atomicAdd(&ctx[c], (a0 + a1 + a2 + a3) * inv);
     }
   }
   __syncthreads();
@@ -362,7 +377,7 @@ int step_launch(const StepCtx& c, const TW* wbase, const int64_t* ids, const int
     float* sk = st.self_kv + (int64_t)i * self_layer;
     float* sv = sk + (int64_t)B * st.max_len * d;
     const size_t smem_self = sizeof(float) * (size_t)(2 * dh + st.max_len + 8);
-    launch_pdl(attn_step_kernel<TW, true>, dim3(H, B), 128, smem_self, c.s, (const float*)qkv, 3 * d, sk, sv, d, st.max_len,
+    launch_pdl(attn_step_kernel<TW, true>, dim3(H, B), 256, smem_self, c.s, (const float*)qkv, 3 * d, sk, sv, d, st.max_len,
                (const float*)nullptr, W(p + ".self.out.kernel"), c.P(p + ".self.out.bias"), x, d, dh, 0, time_dev);
     // encoder-decoder attention block over the pre-projected memory
     if (cf.with_cross_attention && st.Tm > 0) {
@@ -370,7 +385,7 @@ int step_launch(const StepCtx& c, const TW* wbase, const int64_t* ids, const int
                  c.P(p + ".cross.ln.beta"), (const float*)nullptr, cf.ln_eps, W(p + ".cross.q.kernel"), c.P(p + ".cross.q.bias"), qc, B, d, d);
       float* ck = st.cross_kv + (int64_t)i * cross_layer;
       const size_t smem_cross = sizeof(float) * (size_t)(2 * dh + st.Tm + 8);
-      launch_pdl(attn_step_kernel<TW, false>, dim3(H, B), 128, smem_cross, c.s, (const float*)qc, d, ck, ck + d, 2 * d, st.Tm,
+      launch_pdl(attn_step_kernel<TW, false>, dim3(H, B), 256, smem_cross, c.s, (const float*)qc, d, ck, ck + d, 2 * d, st.Tm,
                  st.memory_bias, W(p + ".cross.out.kernel"), c.P(p + ".cross.out.bias"), x, d, dh, st.Tm, time_dev);
     }
     // feed-forward block
@@ -403,7 +418,7 @@ int check_state(const Model& m, const DecodeState& st) {
   B200ST_CHECK(st.max_len >= 1 && st.Tm >= 0, "bad decode lengths");
   B200ST_CHECK(st.self_kv && st.scratch && (st.Tm == 0 || st.cross_kv), "decode state buffers missing");
   const int dh = cf.d / cf.heads;
-  B200ST_CHECK(dh <= 128 && 128 % dh == 0, "decode kernels need a head dim that divides 128");
+  B200ST_CHECK(dh <= 256 && 256 % dh == 0, "decode kernels need a head dim that divides 256");
   const size_t smem = sizeof(float) * (size_t)(2 * dh + (st.Tm > st.max_len ? st.Tm : st.max_len) + 8);
   B200ST_CHECK(smem <= 200 * 1024, "decode: too many keys for the shared-memory score buffer");
   return 0;

@@ -92,7 +92,8 @@ template <typename TX, typename TY, int NV>
 __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const TX* __restrict__ x, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, TY* __restrict__ y,
                                                           float* __restrict__ y32, float* __restrict__ mean_out,
-                                                          float* __restrict__ rstd_out, int64_t rows, int cols, int relu) {
+                                                          float* __restrict__ rstd_out, int64_t rows, int cols, int relu,
+                                                          float* __restrict__ xcopy) {
   pdl_wait();
   pdl_trigger();
   const int lane = threadIdx.x & 31;
@@ -109,7 +110,11 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const TX* __restrict__ 
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = 4 * lane + 128 * i;
-      if (c < cols) { load4<TX>(x + row * cols + c, v[i]); sum += v[i][0] + v[i][1] + v[i][2] + v[i][3]; }
+      if (c < cols) {
+        load4<TX>(x + row * cols + c, v[i]);
+        sum += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+        if (xcopy) store4<float>(xcopy + row * cols + c, v[i]);     // fp32 copy of the input row (residual base of a fused consumer)
+      }
     }
     const float mean = warp_sum(sum) / cols;
     float sq = 0.f;
@@ -143,6 +148,11 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const TX* __restrict__ 
 
 int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
                   float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, cudaStream_t s) {
+  return layernorm_fwd_copy(x, x_dtype, gamma, beta, eps, y, y_dtype, y32, mean, rstd, rows, cols, relu, nullptr, s);
+}
+// + xcopy (optional): fp32 copy of the input rows, written in the same pass
+int layernorm_fwd_copy(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                       float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, float* xcopy, cudaStream_t s) {
   if (rows == 0) return 0;
   const int grid = grid_for(rows, 8 * 2);
   const bool vec = (cols % 4 == 0) && cols <= 1024 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
@@ -150,7 +160,8 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
                    ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) && (!y32 || (reinterpret_cast<uintptr_t>(y32) & 15) == 0);
 #define LN_FWD_VEC(NV)                                                                                                  \
   DISPATCH_DTYPE(x_dtype, TX, DISPATCH_DTYPE(y_dtype, TY,                                                               \
-      (launch_pdl(ln_fwd_vec_kernel<TX, TY, NV>, grid, 256, 0, s, (const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu))))
+      (launch_pdl(ln_fwd_vec_kernel<TX, TY, NV>, grid, 256, 0, s, (const TX*)x, gamma, beta, eps, (TY*)y, y32, mean, rstd, rows, cols, relu, \
+                  (vec && x_dtype == F32 && (reinterpret_cast<uintptr_t>(xcopy) & 15) == 0) ? xcopy : (float*)nullptr))))
   if (vec && cols <= 256) LN_FWD_VEC(2);
   else if (vec && cols <= 512) LN_FWD_VEC(4);
   else if (vec) LN_FWD_VEC(8);
@@ -160,6 +171,10 @@ int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* b
 #undef LN_FWD_VEC
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
+  if (xcopy && !(vec && x_dtype == F32 && (reinterpret_cast<uintptr_t>(xcopy) & 15) == 0)) {
+    B200ST_CHECK(x_dtype == F32, "layernorm_fwd_copy needs fp32 input rows");
+    B200ST_CUDA(cudaMemcpyAsync(xcopy, x, sizeof(float) * (size_t)rows * cols, cudaMemcpyDeviceToDevice, s));
+  }
   return 0;
 }
 

@@ -73,6 +73,12 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream);
 // Dispatch on operand dtype: F32 operands -> SIMT fp32 FMA kernel, BF16 operands -> tcgen05 kernel.
 int gemm(const GemmArgs& g, cudaStream_t stream);
 
+// Fused FFN forward (tc_gemm.cu: fused_mlp_fwd_kernel): x_out(fp32, pre-initialised with the residual) += post-dropout of
+// (dropout(relu(X W1 + b1)) W2 + b2); the hidden activations are also written to F1 for the backward pass.
+bool fused_mlp_supported(int M, int d, int ffn, int dtype);
+int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W1, const float* b1, const void* W2, const float* b2,
+                  DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream);
+
 // Debug knobs for the descriptor probe (tests only). 0 restores defaults.
 struct TcDebug {
   uint32_t mn_lbo_bytes, mn_sbo_bytes, k_lbo_bytes, k_sbo_bytes;

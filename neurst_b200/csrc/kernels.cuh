@@ -13,6 +13,8 @@ extern int64_t g_kernel_launches;
 // mean / rstd (fp32 [rows]) may be null.  (neurst/layers/common_layers.py:64-65,77; audio_modalities.py:73-74,103-104)
 int layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
                   float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, cudaStream_t s);
+int layernorm_fwd_copy(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* y, int y_dtype,
+                       float* y32, float* mean, float* rstd, int64_t rows, int cols, int relu, float* xcopy, cudaStream_t s);
 // dx = [dres +] LN'(dy) ; dgamma/dbeta += ; relu: dy is masked where LN(x)*gamma+beta <= 0 (conv front-end).
 int layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, const float* dres, void* dx, int dx_dtype, float* dgamma,

@@ -213,6 +213,20 @@ struct Ctx {
         side_pending[i] = false;
       }
   }
+  // ---- data-parallel gradient buckets (comm.cu): [lo, hi) of the arena is final -> all-reduce it on the comm stream ----
+  GradSync* sync = nullptr;
+  int64_t sync_hi = 0;       // everything at or above this arena offset has already been handed to NCCL
+  int reduce_down_to(const std::string& first_param) {
+    if (!sync || dry) return 0;
+    const ParamInfo* p = first_param.empty() ? nullptr : info(first_param);
+    const int64_t lo = p ? p->offset : 0;
+    if (lo >= sync_hi) return 0;
+    // weight gradients of this range may still be running on the side stream: the comm stream waits for them directly
+    cudaEvent_t e0 = (side && side_pending[0]) ? side->done[0] : nullptr, e1 = (side && side_pending[1]) ? side->done[1] : nullptr;
+    const int rc = comm_reduce_range(sync, buf.grads, lo, sync_hi, st, e0, e1);
+    sync_hi = lo;
+    return rc;
+  }
   bool dry;        // planning pass: allocate only, launch nothing
   bool training;
   uint64_t seed;
@@ -590,6 +604,18 @@ static int ffn_block_fwd(Ctx& c, const std::string& pre, const float* x_in, floa
   sv.s_ffn = dropout_stream_id(pre + ".ffn_drop"); sv.s_post = dropout_stream_id(pre + ".post_drop");
   sv.h = c.act((int64_t)M * d); sv.mean = c.f32(M); sv.rstd = c.f32(M);
   sv.f1 = c.act((int64_t)M * f);
+  if (fused_mlp_supported(M, d, f, c.adt) && !c.m.cfg.disable_fused_attention) {
+    // one kernel for FFN1 -> ReLU -> dropout -> FFN2 -> dropout -> +residual: the LayerNorm kernel also seeds
+    // x_out with the residual, the fused kernel reduce-adds the rest
+    B200ST_TRY(need_param(c, pre + ".w1")); B200ST_TRY(need_param(c, pre + ".w2"));
+    RUN(layernorm_fwd_copy(x_in, F32, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), cf.ln_eps, sv.h, c.adt, nullptr, sv.mean, sv.rstd,
+                           M, d, 0, x_out, c.st));
+    const DropoutSpec d1 = c.drop(cf.ffn_dropout, sv.s_ffn, (int64_t)M * f);
+    const DropoutSpec d2 = c.drop(cf.postprocess_dropout, sv.s_post, (int64_t)M * d);
+    RUN(fused_mlp_fwd(sv.h, c.adt, M, d, f, c.W(pre + ".w1", 1, f).ptr, c.P(pre + ".b1"), c.W(pre + ".w2", 1, d).ptr, c.P(pre + ".b2"),
+                      d1, d2, sv.f1, x_out, c.st));
+    return 0;
+  }
   RUN(layernorm_fwd(x_in, F32, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), cf.ln_eps, sv.h, c.adt, nullptr, sv.mean, sv.rstd,
                     M, d, 0, c.st));
   GemmEpilogue e1 = gemm_defaults().epi;
@@ -673,7 +699,7 @@ static int encoder_fwd(Ctx& c, const float* x0, const float* bias, int B, int T,
 }
 
 // d_out: fp32 [M,d] gradient wrt encoder output; returns gradient wrt x0 in dx (fp32 [M,d])
-static int encoder_bwd(Ctx& c, const float* d_out, float* dx, float* dx_tmp, Scratch& sc, const EncoderSave& sv) {
+static int encoder_bwd(Ctx& c, const float* d_out, float* dx, float* dx_tmp, Scratch& sc, const EncoderSave& sv, bool buckets = false) {
   const Config& cf = c.m.cfg;
   const int M = sv.B * sv.T, d = cf.d;
   RUN(layernorm_bwd(d_out, F32, sv.x_last, F32, sv.mean, sv.rstd, c.P("enc.out_ln.gamma"), c.P("enc.out_ln.beta"), nullptr, dx, F32,
@@ -687,6 +713,8 @@ static int encoder_bwd(Ctx& c, const float* d_out, float* dx, float* dx_tmp, Scr
     DropoutSpec nd_ffn = no_dropout();
     if (i > 0) { nd_ffn = c.drop(cf.postprocess_dropout, sv.ffn[i - 1].s_post); c.next_drop = &nd_ffn; }
     B200ST_TRY(self_attn_block_bwd(c, p + ".att", dx_tmp, dx, sc, sv.att[i]));
+    // gradient bucket: the upper half of the encoder stack (+ its final LayerNorm) is final after layer enc_layers / 2
+    if (buckets && i == cf.enc_layers / 2 && i > 0) B200ST_TRY(c.reduce_down_to(p + ".att.ln.gamma"));
   }
   return 0;
 }
@@ -925,6 +953,15 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
 
   // =========================== backward ===========================
   if (!c.dry && side_stream().ok && !tc_profile_active()) c.side = &side_stream();
+  if (!c.dry && b.allreduce_grads) {
+    B200ST_CHECK(c.m.sync != nullptr, "allreduce_grads needs b200st_comm_init on this handle");
+    c.sync = c.m.sync;
+    c.sync_hi = c.m.arena_numel;
+    comm_begin_step(c.sync);
+  }
+  // reverse-arena-order buckets only when no tensor receives gradient later than its bucket (text models may tie the
+  // source and target embeddings: one all-reduce at the end)
+  const bool buckets = speech;
   // logits layer: dE += dlogits^T dec_out ; db += colsum ; d_dec_out = dlogits E
   {
     GemmArgs g = gemm_defaults();
@@ -954,9 +991,11 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   RUN(fill_f32(d_enc, 0.f, (int64_t)Ms * d, c.st));
   B200ST_TRY(decoder_bwd(c, d_dec, dy, dy_tmp, d_enc, true, sc, ds));
   RUN(embed_bwd(b.trg_input, dy, c.G("trg.emb"), B, L, d, V, c.drop(cf.postprocess_dropout, dropout_stream_id("dec.in_drop")), c.st));
+  if (buckets) B200ST_TRY(c.reduce_down_to("dec.0.self.ln.gamma"));     // decoder + output layer: ~40 MB under the encoder backward
   float* dx = c.f32((int64_t)Ms * d);
   float* dx_tmp = c.f32((int64_t)Ms * d);
-  B200ST_TRY(encoder_bwd(c, d_enc, dx, dx_tmp, sc, es));
+  B200ST_TRY(encoder_bwd(c, d_enc, dx, dx_tmp, sc, es, buckets));
+  if (buckets) B200ST_TRY(c.reduce_down_to("enc.0.att.ln.gamma"));
   if (speech) {
     B200ST_TRY(speech_front_bwd(c, b.src, dx, fs));
   } else {
@@ -965,6 +1004,10 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
                   c.drop(cf.postprocess_dropout, dropout_stream_id("enc.in_drop")), c.st));
   }
   c.join_side();        // the optimizer / all-reduce on `st` must see every weight gradient
+  if (c.sync) {
+    B200ST_TRY(c.reduce_down_to(""));        // the rest (front-end, or everything when not bucketed)
+    B200ST_TRY(comm_join(c.sync, c.st));
+  }
   return 0;
 }
 

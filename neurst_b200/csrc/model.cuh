@@ -34,12 +34,25 @@ struct ParamInfo {
   int64_t numel;
 };
 
+struct GradSync;     // comm.cu: NCCL communicator + communication stream of a data-parallel replica
+int comm_unique_id(char* out128);
+int comm_init(GradSync** out, const char* id128, int nranks, int rank);
+void comm_destroy(GradSync* g);
+int comm_world(const GradSync* g);
+int64_t comm_reduced_elems(const GradSync* g);
+int comm_calls(const GradSync* g);
+void comm_begin_step(GradSync* g);
+int comm_reduce_range(GradSync* g, float* grads, int64_t lo, int64_t hi, cudaStream_t compute, cudaEvent_t extra0, cudaEvent_t extra1);
+int comm_join(GradSync* g, cudaStream_t compute);
+int comm_broadcast(GradSync* g, float* buf, int64_t n, int root, cudaStream_t compute);
+
 struct Model {
   Config cfg;
   std::vector<ParamInfo> params;
   std::unordered_map<std::string, int> index;
   int64_t arena_numel = 0;
   int adt = F32;              // activation dtype
+  GradSync* sync = nullptr;   // set by b200st_comm_init: gradients are all-reduced inside forward_backward when asked
   int find(const std::string& n) const {
     auto it = index.find(n);
     return it == index.end() ? -1 : it->second;
@@ -79,6 +92,7 @@ struct Batch {
   float* n_tokens;                     // [B]
   float* enc_out;                      // fp32 [B,T',d]
   // b200st_encode: stop after the encoder stack; enc_bias_out receives the additive key bias [B,T'] (0 / -1e9)
+  int allreduce_grads = 0;             // backward: bucketed NCCL all-reduce of the gradient arena, overlapped (needs Model::sync)
   int stop_after_encoder = 0;
   float* enc_bias_out = nullptr;
 };

@@ -412,6 +412,260 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// =============================================================================================================
+// Fused Transformer FFN forward:  x_out += dropout_post( dropout_ffn(relu(X W1 + b1)) W2 + b2 )
+//   neurst/layers/common_layers.py:145-160 (TransformerFFN) inside the pre-norm wrapper (:73-85); X = LN(x_in) (16-bit),
+//   x_out is pre-initialised with the residual x_in by the LayerNorm kernel.
+// One CTA = (128-row tile, slice of the hidden dimension).  The X tile (128 x d, d <= 256) stays in shared memory; the hidden
+// activations of a 128-column chunk are produced in TMEM (GEMM1), turned into the 16-bit A operand of GEMM2 in shared
+// memory by the epilogue warps (bias, ReLU, dropout) — and TMA-stored to HBM only because the backward pass needs them —
+// while GEMM2 accumulates the [128 x d] output tile in TMEM across all chunks.  Only the weights stream (L2 -> smem):
+// 2 x 64 KB per chunk for 2 x 1024 MMA cycles, vs 4 x that for the two unfused GEMMs, and the [M, ffn] hidden tensor is
+// never read back.  Slices of the hidden dimension reduce into x_out with fp32 TMA reduce-add (dropout is a mask: linear).
+//   warp 0: TMA producer (X once, then weight stages in consumption order)     warp 1: MMA issuer
+//   warps 2-9: epilogue (hidden chunk: TMEM -> regs -> smem operand + TMA store; final: TMEM -> regs -> smem -> reduce-add)
+//   TMEM: [0,256) output accumulator, [256,384) / [384,512) hidden accumulators (double buffered)
+//   smem: X 64 KB | H 2 x 32 KB | weight ring 3 x 32 KB (reused as the output staging boxes at the end)
+// =============================================================================================================
+struct MlpParams {
+  int M, d, ffn;
+  int chunks_per_cta;          // 128-column hidden chunks per CTA
+  int splits;                  // hidden slices (gridDim.x = m_tiles * splits)
+  const float* b1; const float* b2;
+  DropoutSpec drop_ffn, drop_post;
+  uint32_t idesc_g1, idesc_g2;
+};
+constexpr int kMlpStages = 3;
+constexpr uint32_t kMlpStageBytes = 32768;
+constexpr uint32_t kMlpXBytes = 65536, kMlpHBytes = 32768;
+constexpr size_t kMlpSmem = 1024 + kMlpXBytes + 2 * kMlpHBytes + kMlpStages * kMlpStageBytes + 256;
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmF1,
+                     const __grid_constant__ CUtensorMap tmOut, const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sX = base;
+  const uint32_t sH = sX + kMlpXBytes;
+  const uint32_t sW = sH + 2 * kMlpHBytes;
+  const uint32_t bars = sW + kMlpStages * kMlpStageBytes;
+  const uint32_t x_full = bars;
+  auto w_full = [&](int s2) { return bars + 8u * (1 + s2); };
+  auto w_empty = [&](int s2) { return bars + 8u * (1 + kMlpStages + s2); };
+  auto ht_full = [&](int b) { return bars + 8u * (1 + 2 * kMlpStages + b); };        // hidden accumulator ready (MMA -> epilogue)
+  auto ht_empty = [&](int b) { return bars + 8u * (3 + 2 * kMlpStages + b); };       // hidden accumulator drained (epilogue -> MMA)
+  auto hs_full = [&](int b) { return bars + 8u * (5 + 2 * kMlpStages + b); };        // hidden operand in smem (epilogue -> MMA)
+  auto hs_empty = [&](int b) { return bars + 8u * (7 + 2 * kMlpStages + b); };       // GEMM2 finished reading it (MMA -> epilogue)
+  const uint32_t out_full = bars + 8u * (9 + 2 * kMlpStages);
+  const uint32_t tmem_slot = bars + 8u * (10 + 2 * kMlpStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const int C = p.chunks_per_cta;
+  const int chunk0 = split * C;
+  const int kbx = p.d / BK;                    // k-blocks of GEMM1 (<= 4)
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmX); ptx::prefetch_tensormap(&tmW1); ptx::prefetch_tensormap(&tmW2);
+    ptx::prefetch_tensormap(&tmF1); ptx::prefetch_tensormap(&tmOut);
+    ptx::mbar_init(x_full, 1);
+    for (int s2 = 0; s2 < kMlpStages; ++s2) { ptx::mbar_init(w_full(s2), 1); ptx::mbar_init(w_empty(s2), 1); }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(ht_full(b), 1); ptx::mbar_init(ht_empty(b), 8);
+      ptx::mbar_init(hs_full(b), 8); ptx::mbar_init(hs_empty(b), 1);
+    }
+    ptx::mbar_init(out_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc_n<512>(tmem_slot); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t tOut = tmem, tH0 = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(x_full, (uint32_t)kbx * kABytes);
+      for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_4d(sX + kb * kABytes, &tmX, x_full, kb * BK, m_blk * BM, 0, 0);
+      int it = 0;
+      auto stage_wait = [&](int& st, uint32_t& dst) {
+        st = it % kMlpStages;
+        ptx::mbar_wait(w_empty(st), (((uint32_t)(it / kMlpStages)) & 1u) ^ 1u);
+        dst = sW + st * kMlpStageBytes;
+        ++it;
+      };
+      auto load_w1 = [&](int c) {          // GEMM1 B operand of chunk c: [K = d rows, N = 128 cols] as 2 k-blocks per stage
+        const int n0 = (chunk0 + c) * 128;
+        for (int s2 = 0; s2 < kbx; s2 += 2) {
+          int st; uint32_t dst;
+          stage_wait(st, dst);
+          const int nkb = min(2, kbx - s2);
+          ptx::mbar_arrive_expect_tx(w_full(st), (uint32_t)nkb * 16384u);
+          for (int j = 0; j < nkb; ++j)
+            for (int i = 0; i < 2; ++i)
+              ptx::tma_load_4d(dst + j * 16384 + i * 8192, &tmW1, w_full(st), n0 + i * 64, (s2 + j) * BK, 0, 0);
+        }
+      };
+      auto load_w2 = [&](int c) {          // GEMM2 B operand of chunk c: [K = 128 hidden rows, N = d cols], one k-block per stage
+        const int k0 = (chunk0 + c) * 128;
+        for (int kb = 0; kb < 2; ++kb) {
+          int st; uint32_t dst;
+          stage_wait(st, dst);
+          ptx::mbar_arrive_expect_tx(w_full(st), (uint32_t)(p.d / 64) * 8192u);
+          for (int i = 0; i < p.d / 64; ++i)
+            ptx::tma_load_4d(dst + i * 8192, &tmW2, w_full(st), i * 64, k0 + kb * BK, 0, 0);
+        }
+      };
+      for (int c = 0; c < C; ++c) { load_w1(c); if (c > 0) load_w2(c - 1); }
+      load_w2(C - 1);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0;
+      auto stage_get = [&](uint32_t& src) {
+        const int st = it % kMlpStages;
+        ptx::mbar_wait(w_full(st), ((uint32_t)(it / kMlpStages)) & 1u);
+        ptx::tc_fence_after();
+        src = sW + st * kMlpStageBytes;
+        ++it;
+        return st;
+      };
+      auto gemm1 = [&](int c) {
+        const int b = c & 1;
+        ptx::mbar_wait(ht_empty(b), (((uint32_t)c >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tH = tH0 + (uint32_t)b * 128u;
+        for (int s2 = 0; s2 < kbx; s2 += 2) {
+          uint32_t src;
+          const int st = stage_get(src);
+          const int nkb = min(2, kbx - s2);
+          for (int j = 0; j < nkb; ++j) {
+            const uint32_t sa = sX + (uint32_t)(s2 + j) * kABytes, sb = src + (uint32_t)j * 16384u;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              ptx::mma_f16_ss(tH, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024),
+                              p.idesc_g1, (s2 + j > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(w_empty(st));
+        }
+        ptx::mma_commit(ht_full(b));
+      };
+      auto gemm2 = [&](int c) {
+        const int b = c & 1;
+        ptx::mbar_wait(hs_full(b), ((uint32_t)c >> 1) & 1u);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          uint32_t src;
+          const int st = stage_get(src);
+          const uint32_t sa = sH + (uint32_t)b * kMlpHBytes + (uint32_t)kb * kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_f16_ss(tOut, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(src + k * 2048, 8192, 1024),
+                            p.idesc_g2, (c > 0 || kb > 0 || k > 0) ? 1u : 0u);
+          ptx::mma_commit(w_empty(st));
+        }
+        ptx::mma_commit(hs_empty(b));
+      };
+      ptx::mbar_wait(x_full, 0);
+      ptx::tc_fence_after();
+      for (int c = 0; c < C; ++c) { gemm1(c); if (c > 0) gemm2(c - 1); }
+      gemm2(C - 1);
+      ptx::mma_commit(out_full);
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = m_blk * BM + quad * 32 + lane;
+    const bool row_ok = m < p.M;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    TcParams hp{};                     // epilogue_math reads alpha / relu / dropout from a TcParams
+    hp.epi.alpha = 1.f; hp.epi.relu = 1; hp.epi.drop = p.drop_ffn;
+    // ---- hidden chunks: TMEM -> bias, ReLU, dropout -> 16-bit A operand of GEMM2 (+ TMA store for the backward pass) ----
+    for (int c = 0; c < C; ++c) {
+      const int b = c & 1;
+      const int n0 = (chunk0 + c) * 128 + half * 64;          // this warp's 64 hidden columns
+      EpiRow er;
+      er.row_ok = row_ok; er.mask = nullptr; er.res = nullptr;
+      er.bias = p.b1 + n0;
+      er.bits = (p.drop_ffn.p > 0.f && row_ok) ? p.drop_ffn.bits + ((uint64_t)((int64_t)m * p.ffn + n0) >> 3) : nullptr;
+      ptx::mbar_wait(ht_full(b), ((uint32_t)c >> 1) & 1u);
+      ptx::tc_fence_after();
+      float v0[32], v1[32];
+      {
+        uint32_t r0[32], r1[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(tH0 + (uint32_t)b * 128u + lane_addr + (uint32_t)(half * 64), r0);
+        ptx::tmem_ld_32x32b_x32(tH0 + (uint32_t)b * 128u + lane_addr + (uint32_t)(half * 64 + 32), r1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ht_empty(b));           // the accumulator can be overwritten by GEMM1 of chunk c + 2
+        epilogue_math<DT == F16 ? OUT_F16 : OUT_BF16>(hp, r0, er, 0, 0.f, v0);
+        epilogue_math<DT == F16 ? OUT_F16 : OUT_BF16>(hp, r1, er, 32, 0.f, v1);
+      }
+      // operand buffer b: GEMM2 of chunk c - 2 has finished reading it, and this warp's own TMA store of chunk c - 2 too
+      ptx::mbar_wait(hs_empty(b), (((uint32_t)c >> 1) & 1u) ^ 1u);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      const uint32_t tile = sH + (uint32_t)b * kMlpHBytes + (uint32_t)half * kABytes + (uint32_t)(quad * 32) * 128u;
+      stage_chunk<DT == F16 ? OUT_F16 : OUT_BF16>(tile, lane, 0, v0);
+      stage_chunk<DT == F16 ? OUT_F16 : OUT_BF16>(tile, lane, 1, v1);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(hs_full(b));
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&tmF1), "r"(tile), "r"(n0), "r"(m_blk * BM + quad * 32), "r"(0), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    // ---- output tile: TMEM -> (+ b2 on slice 0) -> post dropout -> fp32 reduce-add into x_out ----
+    ptx::mbar_wait(out_full, 0);
+    ptx::tc_fence_after();
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    TcParams op{};
+    op.epi.alpha = 1.f; op.epi.drop = p.drop_post;
+    const int ncol = p.d / 2;                                    // columns per half
+    const uint32_t my_stage = sW + (uint32_t)(warp - 2) * 8192u;  // weight ring is free now: 8 warps x 2 x 4 KB boxes
+    for (int bx = 0; bx < ncol / 32; ++bx) {
+      const int co = half * ncol + bx * 32;
+      EpiRow er;
+      er.row_ok = row_ok; er.mask = nullptr; er.res = nullptr;
+      er.bias = (split == 0) ? p.b2 + co : nullptr;
+      er.bits = (p.drop_post.p > 0.f && row_ok) ? p.drop_post.bits + ((uint64_t)((int64_t)m * p.d + co) >> 3) : nullptr;
+      const uint32_t buf = my_stage + (uint32_t)(bx & 1) * 4096u;
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tOut + lane_addr + (uint32_t)co, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+      epilogue_math<OUT_F32>(op, r, er, 0, -INFINITY, v);
+      stage_chunk<OUT_F32>(buf, lane, 0, v);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&tmOut), "r"(buf), "r"(co), "r"(m_blk * BM + quad * 32), "r"(0), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    ptx::tc_fence_before();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
 // -------------------------------------------------------------------------------------------
 // Host side: tensor-map construction (driver entry point fetched at run time; no libcuda link)
 // -------------------------------------------------------------------------------------------
@@ -706,6 +960,50 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
     default: B200ST_FAIL("unsupported BN");
   }
   return rc;
+}
+
+
+// Fused FFN forward (see fused_mlp_fwd_kernel).  X: 16-bit [M, d] (LayerNorm output); W1 [d, ffn], W2 [ffn, d] in the same
+// 16-bit type (TF layouts); F1 out [M, ffn] (saved for the backward pass); x_out fp32 [M, d] must already hold the residual.
+bool fused_mlp_supported(int M, int d, int ffn, int dtype) {
+  return is16(dtype) && (d == 128 || d == 256) && ffn % 128 == 0 && M > 0 && !getenv("B200ST_NO_FUSED_MLP");
+}
+int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W1, const float* b1, const void* W2, const float* b2,
+                  DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream) {
+  B200ST_CHECK(fused_mlp_supported(M, d, ffn, dtype), "fused MLP: unsupported shape / dtype");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B200ST_CUDA(cudaGetDevice(&dev));
+    B200ST_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (drop_ffn.p > 0.f) B200ST_CHECK(drop_ffn.bits != nullptr, "fused MLP needs precomputed dropout bits");
+  if (drop_post.p > 0.f) B200ST_CHECK(drop_post.bits != nullptr, "fused MLP needs precomputed dropout bits");
+  const int m_tiles = ceil_div(M, BM), chunks = ffn / 128;
+  // slices of the hidden dimension: the most CTAs that still fit one wave, with an equal number of chunks per slice
+  int splits = 1;
+  for (int s2 = 1; s2 <= chunks; ++s2)
+    if (chunks % s2 == 0 && (int64_t)m_tiles * s2 <= g_num_sms) splits = s2;
+  MlpParams p{};
+  p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
+  p.b1 = b1; p.b2 = b2; p.drop_ffn = drop_ffn; p.drop_post = drop_post;
+  p.idesc_g1 = ptx::make_idesc_16(128, 0, 1, dtype == BF16, dtype == BF16);
+  p.idesc_g2 = ptx::make_idesc_16(d, 0, 1, dtype == BF16, dtype == BF16);
+  CUtensorMap tx, tw1, tw2, tf1, tout;
+  B200ST_TRY(make_operand_map(GemmOperand{X, dtype, 0, d, 0, 0}, M, d, 1, 1, BM, &tx));
+  B200ST_TRY(make_operand_map(GemmOperand{W1, dtype, 1, ffn, 0, 0}, ffn, d, 1, 1, 64, &tw1));
+  B200ST_TRY(make_operand_map(GemmOperand{W2, dtype, 1, d, 0, 0}, d, ffn, 1, 1, 64, &tw2));
+  B200ST_TRY(make_out_map(F1, dtype, ffn, M, 1, 1, ffn, 0, 0, &tf1));
+  B200ST_TRY(make_out_map(x_out, F32, d, M, 1, 1, d, 0, 0, &tout));
+  auto kern = dtype == F16 ? fused_mlp_fwd_kernel<F16> : fused_mlp_fwd_kernel<BF16>;
+  static bool attr[2] = {false, false};
+  if (!attr[dtype == F16]) {
+    B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem));
+    attr[dtype == F16] = true;
+  }
+  launch_pdl(kern, m_tiles * splits, kThreads, kMlpSmem, stream, tx, tw1, tw2, tf1, tout, p);
+  ++g_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
 }
 
 void tc_profile_begin() {

@@ -138,6 +138,31 @@ class Runtime:
         b.workspace_bytes = ws.numel() - (aligned - base)
         return b
 
+    # ---- data parallelism: NCCL communicator owned by the library (b200st_comm_*) ----------------------------------
+    def comm_init(self, dist):
+        """One communicator per replica: rank 0 creates the NCCL unique id, it travels over the existing process group
+        (host channel only), every rank joins.  After this `run(..., allreduce=True)` / graph steps all-reduce the
+        gradient arena inside the library, bucketed and overlapped with the backward pass."""
+        world, rank = dist.get_world_size(), dist.get_rank()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            L.check(self.lib.b200st_comm_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        ident = bytes(t.cpu().tolist())
+        L.check(self.lib.b200st_comm_init(self.handle, ident, world, rank))
+        self.comm_world = world
+        return self
+
+    def comm_broadcast_parameters(self, root=0):
+        L.check(self.lib.b200st_comm_broadcast(self.handle, _ptr(self.params), self.numel, int(root), L._stream()))
+        self._shadow_stale = True
+
+    def comm_stats(self):
+        n, c, w = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        L.check(self.lib.b200st_comm_stats(self.handle, C.byref(n), C.byref(c), C.byref(w)))
+        return dict(reduced_elems=n.value, calls=c.value, world=w.value)
+
     def run(self, batch, backward):
         """batch: dict of CUDA tensors: src|src_ids, src_length|src_padding, trg_input[, trg, trg_length] (+ opts)."""
         if self._shadow_stale:
@@ -191,6 +216,11 @@ class Runtime:
         if need <= 0:
             raise L.B200STError("workspace planning failed: " + self.lib.b200st_last_error().decode())
         bufs = self._buffers(need, backward)
+        if backward and batch.get("allreduce", False):
+            opts = L.StepOpts()
+            opts.allreduce_grads = 1
+            L.check(self.lib.b200st_train_step(self.handle, C.byref(bufs), C.byref(bt), C.byref(opts), L._stream()))
+            return out
         fn = self.lib.b200st_forward_backward if backward else self.lib.b200st_forward
         L.check(fn(self.handle, C.byref(bufs), C.byref(bt), L._stream()))
         return out
@@ -242,7 +272,8 @@ class GraphedTrainStep:
     `__call__` refreshes, and the dropout seed is read by the kernels from a device word (`seed_dev`), so every replay
     draws fresh masks.  Gradients accumulate into the runtime's gradient arena exactly as in the eager path."""
 
-    def __init__(self, rt, B, T, Lq):
+    def __init__(self, rt, B, T, Lq, allreduce=False):
+        self.allreduce = bool(allreduce)
         cfg = rt.config
         if cfg.model_type != L.MODEL_SPEECH:
             raise L.B200STError("GraphedTrainStep supports the SpeechTransformer handle")
@@ -275,6 +306,11 @@ class GraphedTrainStep:
         self.graph = None
 
     def _launch(self):
+        if self.allreduce:      # the NCCL all-reduces on the library's communication stream become branches of the graph
+            opts = L.StepOpts()
+            opts.allreduce_grads = 1
+            L.check(self.rt.lib.b200st_train_step(self.rt.handle, C.byref(self.bufs), C.byref(self.bt), C.byref(opts), L._stream()))
+            return
         L.check(self.rt.lib.b200st_forward_backward(self.rt.handle, C.byref(self.bufs), C.byref(self.bt), L._stream()))
 
     def capture(self):

@@ -50,7 +50,7 @@ class DataParallelTrainer:
     initial parameter broadcast and scalar metric reduction."""
 
     def __init__(self, model, optimizer_params=None, lr_schedule_params=None, update_cycle=1, grad_buckets=1,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, clip_value=None, clip_norm=None, summary_steps=0, logger=None):
         self.model = model
         self.rt = model.runtime
         op = optimizer_params or {}
@@ -66,15 +66,25 @@ class DataParallelTrainer:
         self.grad_buckets = max(1, int(grad_buckets))
         self.use_cuda_graph = bool(use_cuda_graph)
         self._graphs = {}
+        # gradient clipping of the reference's step (exps/trainer.py:74-75,130-131 -> gradaccum_keras_model.py:228-233)
+        self.clip_value, self.clip_norm = clip_value, clip_norm
+        # NCCL inside the library when the job runs on GPUs (one communicator per replica); torch.distributed stays the
+        # transport only for the gloo / CPU stand-in used by the host-logic tests
+        self.lib_comm = bool(self.dist and hasattr(self.rt, "comm_init") and self.dist.get_backend() == "nccl")
+        if self.lib_comm:
+            self.rt.comm_init(self.dist)
+        self.meter = ThroughputMeter(summary_steps, self.world, logger) if summary_steps else None
 
     def broadcast_parameters(self):
         """rank 0 -> all (hvd BroadcastGlobalVariablesCallback, exps/trainer.py:285)."""
-        if self.dist:
+        if self.lib_comm:
+            self.rt.comm_broadcast_parameters(0)
+        elif self.dist:
             self.dist.broadcast(self.rt.params, src=0)
             self.rt._shadow_stale = True
 
     def _allreduce_grads(self):
-        if self.dist:
+        if self.dist and not self.lib_comm:        # lib_comm: already reduced inside b200st_train_step, overlapped
             allreduce_sum_(self.rt.grads, self.dist, self.grad_buckets)
 
     def train_step(self, inputs, seed=None):
@@ -83,15 +93,21 @@ class DataParallelTrainer:
         if seed is not None:
             # independent dropout draws per replica (the reference's replicas seed their own RNG streams)
             b["seed"] = int(seed) * self.world + self.rank
+        last_micro = (self._micro + 1) % self.update_cycle == 0
+        sync_now = self.lib_comm and last_micro          # gradients are all-reduced by the step that completes a cycle
         if self.use_cuda_graph:
             from neurst_b200.runtime import GraphedTrainStep
-            key = (b["src"].shape[0], b["src"].shape[1], b["trg_input"].shape[1])   # one graph per shape bucket
+            key = (b["src"].shape[0], b["src"].shape[1], b["trg_input"].shape[1], sync_now)   # one graph per shape bucket
             if key not in self._graphs:
-                self._graphs[key] = GraphedTrainStep(self.rt, *key).capture()
+                self._graphs[key] = GraphedTrainStep(self.rt, *key[:3], allreduce=sync_now).capture()
             self._seed_ctr = getattr(self, "_seed_ctr", 0) + 1
             out = self._graphs[key](b, b.get("seed", self._seed_ctr * self.world + self.rank))
         else:
+            if sync_now:
+                b["allreduce"] = True
             out = self.model.forward_backward(b, is_training=True, loss_scale=1.0)
+        if self.meter is not None:
+            self.meter.add(inputs)
         self._micro += 1
         if self._micro % self.update_cycle == 0:
             self._allreduce_grads()
@@ -99,8 +115,53 @@ class DataParallelTrainer:
             self.global_step += 1
             # GradientAccumulator averages over update_cycle (gradaccum_keras_model.py:62-109); hvd.Average over ranks
             scale = 1.0 / (self.world * self.update_cycle)
-            self.rt.adam_step(lr, self.global_step, self.beta1, self.beta2, self.eps, grad_scale=scale, zero_grad=True)
+            kw = {}
+            if self.clip_value or self.clip_norm:
+                kw = dict(clip_value=self.clip_value, clip_norm=self.clip_norm)
+            self.rt.adam_step(lr, self.global_step, self.beta1, self.beta2, self.eps, grad_scale=scale, zero_grad=True, **kw)
+            if self.meter is not None:
+                self.meter.step_end(self.global_step, out["loss"], lr)
         return out["loss"]
+
+
+class ThroughputMeter:
+    """MetricReductionCallback's speed lines (neurst/training/callbacks.py:209-245): every `summary_steps` updates log
+    'Update N TrainingLoss=... Speed x secs/step y steps/sec' and a dict with, for every SUM metric of the task
+    (src_tokens = input frames, src_real_tokens = sum(src_length), trg_tokens, trg_real_tokens, samples —
+    neurst/layers/metric_layers/token_metric_layers.py:59-65), `<metric>_per_step` and `<metric>_per_sec` scaled by the number
+    of replicas."""
+
+    def __init__(self, summary_steps, world=1, logger=None):
+        import logging
+        self.n, self.world = max(1, int(summary_steps)), world
+        self.log = logger or logging.getLogger("neurst_b200").info
+        self.acc = {}
+        self.t0 = time.time()
+        self.last = None
+
+    def add(self, inputs):
+        src, trg = inputs["src"], inputs["trg_input"]
+        m = {"src_tokens": src.shape[0] * src.shape[1], "trg_tokens": trg.shape[0] * trg.shape[1], "samples": src.shape[0]}
+        if "src_length" in inputs:
+            m["src_real_tokens"] = inputs["src_length"]
+        if "trg_length" in inputs:
+            m["trg_real_tokens"] = inputs["trg_length"]
+        for k, v in m.items():
+            self.acc.setdefault(k, []).append(v)
+
+    def step_end(self, step, loss, lr):
+        if step % self.n != 0:
+            return None
+        dt = max(time.time() - self.t0, 1e-9)
+        tot = {k: float(sum(float(x.sum()) if torch.is_tensor(x) else x for x in v)) * self.world for k, v in self.acc.items()}
+        self.log("Update %d\tTrainingLoss=%.2f\tSpeed %.3f secs/step %.1f steps/sec" % (step, float(loss), dt / self.n, self.n / dt))
+        line = {"step": step, "lr": lr}
+        for k, v in tot.items():
+            line[k + "_per_step"] = v / self.n
+            line[k + "_per_sec"] = v / dt
+        self.log(str(line))
+        self.acc, self.t0, self.last = {}, time.time(), line
+        return line
 
 
 class HostPipeline:
