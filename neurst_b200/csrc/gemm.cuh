@@ -79,6 +79,9 @@ bool fused_mlp_supported(int M, int d, int ffn, int dtype);
 int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W1, const float* b1, const void* W2, const float* b2,
                   DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream);
 
+int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* W1, const void* W2, const void* F1, float scale,
+                  void* dF1, float* dH, cudaStream_t stream);
+
 // Debug knobs for the descriptor probe (tests only). 0 restores defaults.
 struct TcDebug {
   uint32_t mn_lbo_bytes, mn_sbo_bytes, k_lbo_bytes, k_sbo_bytes;

@@ -636,6 +636,16 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
   if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
   else RUN(cast_dropout(dx_out, sc.dY, c.adt, (int64_t)M * d, c.drop(cf.postprocess_dropout, sv.s_post), c.st));
   B200ST_TRY(linear_wgrad(c, sv.f1, f, sc.dY, d, M, f, d, pre + ".w2", pre + ".b2"));
+  if (fused_mlp_supported(M, d, f, c.adt) && !c.m.cfg.disable_fused_attention && !getenv("B200ST_NO_FUSED_MLP_BWD")) {
+    // data-gradient chain in one kernel: dF1 = (dY W2^T) * relu'/dropout' (written for the W1 weight gradient), dh = dF1 W1^T
+    const DropoutSpec fd = c.drop(cf.ffn_dropout, sv.s_ffn);
+    RUN(cudaMemsetAsync(sc.dh, 0, sizeof(float) * (size_t)M * d, c.st) == cudaSuccess ? 0 : 1);
+    RUN(fused_mlp_bwd(sc.dY, c.adt, M, d, f, c.W(pre + ".w1", 0, f).ptr, c.W(pre + ".w2", 0, d).ptr, sv.f1,
+                      fd.p > 0.f ? fd.scale : 1.f, sc.dF1, sc.dh, c.st));
+    B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dF1, f, M, d, f, pre + ".w1", pre + ".b1"));
+    B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
+    return 0;
+  }
   GemmEpilogue e1 = gemm_defaults().epi;
   e1.mask_src = sv.f1; e1.mask_dtype = c.adt; e1.mask_ld = f;      // relu' and ffn-dropout mask: stored f1 > 0
   const DropoutSpec fd = c.drop(cf.ffn_dropout, sv.s_ffn);

@@ -435,13 +435,19 @@ struct MlpParams {
   const float* b1; const float* b2;
   DropoutSpec drop_ffn, drop_post;
   uint32_t idesc_g1, idesc_g2;
+  // backward (dgrad chain) variant: hidden epilogue = alpha * acc masked by (mask_src > 0), no bias / ReLU / dropout bits
+  int relu;
+  float alpha;
+  const void* mask_src; int64_t mask_ld;
 };
 constexpr int kMlpStages = 3;
 constexpr uint32_t kMlpStageBytes = 32768;
 constexpr uint32_t kMlpXBytes = 65536, kMlpHBytes = 32768;
-constexpr size_t kMlpSmem = 1024 + kMlpXBytes + 2 * kMlpHBytes + kMlpStages * kMlpStageBytes + 256;
+constexpr size_t kMlpSmem = 1024 + kMlpXBytes + 2 * kMlpHBytes + kMlpStages * kMlpStageBytes + 256 + 1024;
 
-template <int DT>
+// B_MN: weights as MN-major B operands (forward: W1 [d, ffn], W2 [ffn, d] in the TF [in, out] layout) or K-major (backward:
+// the same arrays read transposed: G1 uses W2 rows = hidden units, G2 uses W1 rows = model dims)
+template <int DT, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmF1,
@@ -461,6 +467,7 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   auto hs_empty = [&](int b) { return bars + 8u * (7 + 2 * kMlpStages + b); };       // GEMM2 finished reading it (MMA -> epilogue)
   const uint32_t out_full = bars + 8u * (9 + 2 * kMlpStages);
   const uint32_t tmem_slot = bars + 8u * (10 + 2 * kMlpStages);
+  const uint32_t bias_off = bars + 256u;           // 1 KB: [2][128] bias floats of the current / next hidden chunk
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -508,9 +515,14 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           stage_wait(st, dst);
           const int nkb = min(2, kbx - s2);
           ptx::mbar_arrive_expect_tx(w_full(st), (uint32_t)nkb * 16384u);
-          for (int j = 0; j < nkb; ++j)
-            for (int i = 0; i < 2; ++i)
-              ptx::tma_load_4d(dst + j * 16384 + i * 8192, &tmW1, w_full(st), n0 + i * 64, (s2 + j) * BK, 0, 0);
+          for (int j = 0; j < nkb; ++j) {
+            if (B_MN) {
+              for (int i = 0; i < 2; ++i)
+                ptx::tma_load_4d(dst + j * 16384 + i * 8192, &tmW1, w_full(st), n0 + i * 64, (s2 + j) * BK, 0, 0);
+            } else {
+              ptx::tma_load_4d(dst + j * 16384, &tmW1, w_full(st), (s2 + j) * BK, n0, 0, 0);      // [128 rows x 64 k]
+            }
+          }
         }
       };
       auto load_w2 = [&](int c) {          // GEMM2 B operand of chunk c: [K = 128 hidden rows, N = d cols], one k-block per stage
@@ -519,8 +531,12 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           int st; uint32_t dst;
           stage_wait(st, dst);
           ptx::mbar_arrive_expect_tx(w_full(st), (uint32_t)(p.d / 64) * 8192u);
-          for (int i = 0; i < p.d / 64; ++i)
-            ptx::tma_load_4d(dst + i * 8192, &tmW2, w_full(st), i * 64, k0 + kb * BK, 0, 0);
+          if (B_MN) {
+            for (int i = 0; i < p.d / 64; ++i)
+              ptx::tma_load_4d(dst + i * 8192, &tmW2, w_full(st), i * 64, k0 + kb * BK, 0, 0);
+          } else {
+            ptx::tma_load_4d(dst, &tmW2, w_full(st), k0 + kb * BK, 0, 0, 0);                        // [d rows x 64 k]
+          }
         }
       };
       for (int c = 0; c < C; ++c) { load_w1(c); if (c > 0) load_w2(c - 1); }
@@ -550,7 +566,8 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const uint32_t sa = sX + (uint32_t)(s2 + j) * kABytes, sb = src + (uint32_t)j * 16384u;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              ptx::mma_f16_ss(tH, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024),
+              ptx::mma_f16_ss(tH, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                              B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024) : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024),
                               p.idesc_g1, (s2 + j > 0 || k > 0) ? 1u : 0u);
           }
           ptx::mma_commit(w_empty(st));
@@ -567,7 +584,8 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t sa = sH + (uint32_t)b * kMlpHBytes + (uint32_t)kb * kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            ptx::mma_f16_ss(tOut, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(src + k * 2048, 8192, 1024),
+            ptx::mma_f16_ss(tOut, ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024),
+                            B_MN ? ptx::make_smem_desc_sw128(src + k * 2048, 8192, 1024) : ptx::make_smem_desc_sw128(src + k * 32, 16, 1024),
                             p.idesc_g2, (c > 0 || kb > 0 || k > 0) ? 1u : 0u);
           ptx::mma_commit(w_empty(st));
         }
@@ -584,19 +602,54 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int m = m_blk * BM + quad * 32 + lane;
     const bool row_ok = m < p.M;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    TcParams hp{};                     // epilogue_math reads alpha / relu / dropout from a TcParams
-    hp.epi.alpha = 1.f; hp.epi.relu = 1; hp.epi.drop = p.drop_ffn;
-    // ---- hidden chunks: TMEM -> bias, ReLU, dropout -> 16-bit A operand of GEMM2 (+ TMA store for the backward pass) ----
+    // ---- hidden chunks: TMEM -> bias, ReLU, dropout (forward) / relu'-dropout' mask (backward) -> 16-bit A operand of GEMM2
+    // (+ TMA store: the backward pass / the W1 weight gradient need it).  With 230 KB of shared memory there is no L1 left, so
+    // every global operand of the epilogue is fetched one chunk AHEAD: the 64 bias values of each column half go through a
+    // 1 KB double buffer in shared memory (loaded by the quad-0 warps), the dropout keep-words / the 16-bit mask row of the
+    // thread sit in registers across the wait for the accumulator.
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_off - ptx::smem_u32(smem_raw)));      // [2][128]
+    const bool use_bits = p.drop_ffn.p > 0.f;
+    const float dscale = use_bits ? p.drop_ffn.scale : 1.f;
+    const float hidden_floor = p.relu ? 0.f : -INFINITY;
+    auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    uint32_t keep_n[2] = {0xffffffffu, 0xffffffffu};
+    uint4 mask_n[B_MN ? 1 : 8];
+    auto prefetch = [&](int c) {          // global operands of chunk c
+      const int n0 = (chunk0 + c) * 128 + half * 64;
+      if (quad == 0 && p.b1) {
+        bias_s[(c & 1) * 128 + half * 64 + lane] = __ldg(p.b1 + n0 + lane);
+        bias_s[(c & 1) * 128 + half * 64 + 32 + lane] = __ldg(p.b1 + n0 + 32 + lane);
+      }
+      if (use_bits && row_ok) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.drop_ffn.bits + ((uint64_t)((int64_t)m * p.ffn + n0) >> 3)));
+        keep_n[0] = w.x; keep_n[1] = w.y;
+      }
+      if (!B_MN) {
+        if (p.mask_src && row_ok) {
+          const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(p.mask_src) + ((int64_t)m * p.mask_ld + n0) * 2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mask_n[j] = __ldg(mp + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mask_n[j] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+    prefetch(0);
+    epi_bar();
     for (int c = 0; c < C; ++c) {
       const int b = c & 1;
       const int n0 = (chunk0 + c) * 128 + half * 64;          // this warp's 64 hidden columns
-      EpiRow er;
-      er.row_ok = row_ok; er.mask = nullptr; er.res = nullptr;
-      er.bias = p.b1 + n0;
-      er.bits = (p.drop_ffn.p > 0.f && row_ok) ? p.drop_ffn.bits + ((uint64_t)((int64_t)m * p.ffn + n0) >> 3) : nullptr;
+      const uint32_t keep[2] = {keep_n[0], keep_n[1]};
+      uint4 mask_c[B_MN ? 1 : 8];
+      if (!B_MN) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mask_c[j] = mask_n[j];
+      }
+      if (c + 1 < C) prefetch(c + 1);                          // in flight across the wait for the accumulator
       ptx::mbar_wait(ht_full(b), ((uint32_t)c >> 1) & 1u);
       ptx::tc_fence_after();
-      float v0[32], v1[32];
+      float v[2][32];
       {
         uint32_t r0[32], r1[32];
         __syncwarp();
@@ -606,16 +659,47 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ht_empty(b));           // the accumulator can be overwritten by GEMM1 of chunk c + 2
-        epilogue_math<DT == F16 ? OUT_F16 : OUT_BF16>(hp, r0, er, 0, 0.f, v0);
-        epilogue_math<DT == F16 ? OUT_F16 : OUT_BF16>(hp, r1, er, 32, 0.f, v1);
+        const float* bs = bias_s + b * 128 + half * 64;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t (&r)[32] = hh ? r1 : r0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.b1) bb = *reinterpret_cast<const float4*>(bs + hh * 32 + 4 * j4);          // broadcast LDS.128
+            v[hh][4 * j4 + 0] = fmaxf(fmaf(__uint_as_float(r[4 * j4 + 0]), p.alpha, bb.x), hidden_floor);
+            v[hh][4 * j4 + 1] = fmaxf(fmaf(__uint_as_float(r[4 * j4 + 1]), p.alpha, bb.y), hidden_floor);
+            v[hh][4 * j4 + 2] = fmaxf(fmaf(__uint_as_float(r[4 * j4 + 2]), p.alpha, bb.z), hidden_floor);
+            v[hh][4 * j4 + 3] = fmaxf(fmaf(__uint_as_float(r[4 * j4 + 3]), p.alpha, bb.w), hidden_floor);
+          }
+          if (use_bits) {
+            const uint32_t k32 = keep[hh];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[hh][j] = ((k32 >> j) & 1u) ? v[hh][j] * dscale : 0.f;
+          }
+          if (!B_MN) {
+            // 16-bit mask source (bf16 / fp16): "> 0" <=> sign clear and magnitude bits non-zero
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = mask_c[hh * 4 + j];
+              const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+                if (!(lo != 0u && lo < 0x8000u)) v[hh][8 * j + 2 * i] = 0.f;
+                if (!(hi != 0u && hi < 0x8000u)) v[hh][8 * j + 2 * i + 1] = 0.f;
+              }
+            }
+          }
+        }
       }
       // operand buffer b: GEMM2 of chunk c - 2 has finished reading it, and this warp's own TMA store of chunk c - 2 too
       ptx::mbar_wait(hs_empty(b), (((uint32_t)c >> 1) & 1u) ^ 1u);
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
       const uint32_t tile = sH + (uint32_t)b * kMlpHBytes + (uint32_t)half * kABytes + (uint32_t)(quad * 32) * 128u;
-      stage_chunk<DT == F16 ? OUT_F16 : OUT_BF16>(tile, lane, 0, v0);
-      stage_chunk<DT == F16 ? OUT_F16 : OUT_BF16>(tile, lane, 1, v1);
+      stage_chunk<DT == F16 ? OUT_F16 : OUT_BF16>(tile, lane, 0, v[0]);
+      stage_chunk<DT == F16 ? OUT_F16 : OUT_BF16>(tile, lane, 1, v[1]);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -624,22 +708,29 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                      ::"l"(&tmF1), "r"(tile), "r"(n0), "r"(m_blk * BM + quad * 32), "r"(0), "r"(0) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      epi_bar();                 // bias of chunk c + 1 is in shared memory; buffer (c & 1) may be refilled next iteration
     }
+    // output bias (slice 0 only) through the same 1 KB of shared memory, keep-words of the output tile in registers
+    const int ncol = p.d / 2;                                    // columns per half
+    const bool add_b2 = split == 0 && p.b2 != nullptr;
+    if (add_b2 && (int)threadIdx.x - 64 < p.d) bias_s[threadIdx.x - 64] = __ldg(p.b2 + (threadIdx.x - 64));
+    uint32_t keep_o[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (p.drop_post.p > 0.f && row_ok) {
+      const uint32_t* kp = reinterpret_cast<const uint32_t*>(p.drop_post.bits + ((uint64_t)((int64_t)m * p.d + half * ncol) >> 3));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < ncol / 32) keep_o[j] = __ldg(kp + j);
+    }
+    epi_bar();
     // ---- output tile: TMEM -> (+ b2 on slice 0) -> post dropout -> fp32 reduce-add into x_out ----
     ptx::mbar_wait(out_full, 0);
     ptx::tc_fence_after();
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
-    TcParams op{};
-    op.epi.alpha = 1.f; op.epi.drop = p.drop_post;
-    const int ncol = p.d / 2;                                    // columns per half
+    const float pscale = p.drop_post.p > 0.f ? p.drop_post.scale : 1.f;
     const uint32_t my_stage = sW + (uint32_t)(warp - 2) * 8192u;  // weight ring is free now: 8 warps x 2 x 4 KB boxes
+#pragma unroll 1
     for (int bx = 0; bx < ncol / 32; ++bx) {
       const int co = half * ncol + bx * 32;
-      EpiRow er;
-      er.row_ok = row_ok; er.mask = nullptr; er.res = nullptr;
-      er.bias = (split == 0) ? p.b2 + co : nullptr;
-      er.bits = (p.drop_post.p > 0.f && row_ok) ? p.drop_post.bits + ((uint64_t)((int64_t)m * p.d + co) >> 3) : nullptr;
       const uint32_t buf = my_stage + (uint32_t)(bx & 1) * 4096u;
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
@@ -647,7 +738,16 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       ptx::tmem_ld_32x32b_x32(tOut + lane_addr + (uint32_t)co, r);
       ptx::tmem_ld_wait();
       float v[32];
-      epilogue_math<OUT_F32>(op, r, er, 0, -INFINITY, v);
+      const uint32_t k32 = keep_o[bx & 3];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_b2) bb = *reinterpret_cast<const float4*>(bias_s + co + 4 * j4);
+        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + bb.x; v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + bb.z; v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((k32 >> j) & 1u) ? v[j] * pscale : 0.f;
       stage_chunk<OUT_F32>(buf, lane, 0, v);
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -986,6 +1086,7 @@ int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W
   MlpParams p{};
   p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
   p.b1 = b1; p.b2 = b2; p.drop_ffn = drop_ffn; p.drop_post = drop_post;
+  p.relu = 1; p.alpha = 1.f; p.mask_src = nullptr; p.mask_ld = 0;
   p.idesc_g1 = ptx::make_idesc_16(128, 0, 1, dtype == BF16, dtype == BF16);
   p.idesc_g2 = ptx::make_idesc_16(d, 0, 1, dtype == BF16, dtype == BF16);
   CUtensorMap tx, tw1, tw2, tf1, tout;
@@ -994,7 +1095,45 @@ int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W
   B200ST_TRY(make_operand_map(GemmOperand{W2, dtype, 1, d, 0, 0}, d, ffn, 1, 1, 64, &tw2));
   B200ST_TRY(make_out_map(F1, dtype, ffn, M, 1, 1, ffn, 0, 0, &tf1));
   B200ST_TRY(make_out_map(x_out, F32, d, M, 1, 1, d, 0, 0, &tout));
-  auto kern = dtype == F16 ? fused_mlp_fwd_kernel<F16> : fused_mlp_fwd_kernel<BF16>;
+  auto kern = dtype == F16 ? fused_mlp_fwd_kernel<F16, true> : fused_mlp_fwd_kernel<BF16, true>;
+  static bool attr[2] = {false, false};
+  if (!attr[dtype == F16]) {
+    B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem));
+    attr[dtype == F16] = true;
+  }
+  launch_pdl(kern, m_tiles * splits, kThreads, kMlpSmem, stream, tx, tw1, tw2, tf1, tout, p);
+  ++g_launches;
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+// Fused FFN backward, data-gradient chain: dF1 = scale * (dY W2^T) masked by (F1 > 0)  [written for the W1 weight gradient],
+// dH += dF1 W1^T (fp32, dH must be zero-initialised).  Same kernel, weights read as K-major B operands.
+int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* W1, const void* W2, const void* F1, float scale,
+                  void* dF1, float* dH, cudaStream_t stream) {
+  B200ST_CHECK(fused_mlp_supported(M, d, ffn, dtype), "fused MLP: unsupported shape / dtype");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B200ST_CUDA(cudaGetDevice(&dev));
+    B200ST_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int m_tiles = ceil_div(M, BM), chunks = ffn / 128;
+  int splits = 1;
+  for (int s2 = 1; s2 <= chunks; ++s2)
+    if (chunks % s2 == 0 && (int64_t)m_tiles * s2 <= g_num_sms) splits = s2;
+  MlpParams p{};
+  p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
+  p.b1 = nullptr; p.b2 = nullptr; p.drop_ffn = no_dropout(); p.drop_post = no_dropout();
+  p.relu = 0; p.alpha = scale; p.mask_src = F1; p.mask_ld = ffn;
+  p.idesc_g1 = ptx::make_idesc_16(128, 0, 0, dtype == BF16, dtype == BF16);
+  p.idesc_g2 = ptx::make_idesc_16(d, 0, 0, dtype == BF16, dtype == BF16);
+  CUtensorMap tx, tw1, tw2, tf1, tout;
+  B200ST_TRY(make_operand_map(GemmOperand{dY, dtype, 0, d, 0, 0}, M, d, 1, 1, BM, &tx));
+  B200ST_TRY(make_operand_map(GemmOperand{W2, dtype, 0, d, 0, 0}, ffn, d, 1, 1, 128, &tw1));     // G1: rows = hidden units, k = d
+  B200ST_TRY(make_operand_map(GemmOperand{W1, dtype, 0, ffn, 0, 0}, d, ffn, 1, 1, d, &tw2));      // G2: rows = model dims, k = hidden
+  B200ST_TRY(make_out_map(dF1, dtype, ffn, M, 1, 1, ffn, 0, 0, &tf1));
+  B200ST_TRY(make_out_map(dH, F32, d, M, 1, 1, d, 0, 0, &tout));
+  auto kern = dtype == F16 ? fused_mlp_fwd_kernel<F16, false> : fused_mlp_fwd_kernel<BF16, false>;
   static bool attr[2] = {false, false};
   if (!attr[dtype == F16]) {
     B200ST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMlpSmem));
