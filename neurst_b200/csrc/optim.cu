@@ -21,30 +21,38 @@ __device__ __forceinline__ int tensor_of(const TensorTable& tt, uint32_t e8) {  
   return lo;
 }
 
-// sumsq[t] += sum of g^2 over tensor t (block = 2048 consecutive elements; tensors start at multiples of 8 elements)
+// sumsq[t] += sum of g^2 over tensor t.  A warp owns 1024 consecutive elements per iteration (4 x 16-byte loads per lane in
+// flight, coalesced 512-byte rows); tensors start at multiples of 8 elements, so a lane's 4-element vector never straddles
+// two tensors.  Usually the whole warp range lies inside one tensor: one atomic per warp.
 __global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict__ g, int64_t n, const __grid_constant__ TensorTable tt,
                                                          float* __restrict__ sumsq) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float wsum[8];
-  for (int64_t base = (int64_t)blockIdx.x * 2048; base < n; base += (int64_t)gridDim.x * 2048) {
-    const int64_t i = base + (int64_t)threadIdx.x * 8;
-    float acc = 0.f;
-    int t = -1;
-    if (i < n) {
-      t = tensor_of(tt, (uint32_t)(i >> 3));
-      const float4 a = *reinterpret_cast<const float4*>(g + i);
-      const float4 b = (i + 4 < n) ? *reinterpret_cast<const float4*>(g + i + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      acc = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n4 = n >> 2;                       // arenas are padded to multiples of 8 elements
+  for (int64_t base = warp_id * 256; base < n4; base += n_warps * 256) {      // in float4 units: 256 vectors = 1024 elements
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t i = base + j * 32 + lane;
+      v[j] = i < n4 ? __ldg(reinterpret_cast<const float4*>(g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // a warp covers 256 consecutive elements: usually one tensor -> one atomic per warp; otherwise per lane
-    const int t0 = __shfl_sync(0xffffffffu, t, 0);
-    const bool uniform = __all_sync(0xffffffffu, t == t0 || t < 0);
-    if (uniform) {
-      const float w = warp_sum(acc);
-      if ((threadIdx.x & 31) == 0 && t0 >= 0) atomicAdd(sumsq + t0, w);
-    } else if (t >= 0) {
-      atomicAdd(sumsq + t, acc);
+    const int64_t last = (base + 255 < n4 ? base + 255 : n4 - 1);
+    const int t_first = tensor_of(tt, (uint32_t)(base >> 1)), t_last = tensor_of(tt, (uint32_t)(last >> 1));
+    if (t_first == t_last) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(sumsq + t_first, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t i = base + j * 32 + lane;
+        if (i < n4) atomicAdd(sumsq + tensor_of(tt, (uint32_t)(i >> 1)), v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w);
+      }
     }
   }
 }
@@ -173,8 +181,9 @@ int optimizer_step(const OptimArgs& a, const TensorTable& tt, cudaStream_t s) {
   if (need_stats) {
     B200ST_CHECK(a.tensor_sumsq != nullptr, "clip_norm / dynamic loss scale need the tensor_sumsq scratch [n_tensors + 1]");
     B200ST_CHECK(tt.n > 0 && tt.n <= 512, "clip_norm / dynamic loss scale support up to 512 parameter tensors");
+    B200ST_CHECK(a.n % 8 == 0, "clip_norm / dynamic loss scale need an arena padded to a multiple of 8 elements");
     B200ST_CUDA(cudaMemsetAsync(a.tensor_sumsq, 0, sizeof(float) * (size_t)(tt.n + 1), s));
-    launch_pdl(grad_stats_kernel, grid_for(a.n, 2048, 148 * 8), 256, 0, s, (const float*)a.g, a.n, tt, a.tensor_sumsq);
+    launch_pdl(grad_stats_kernel, grid_for(a.n, 8192, 148 * 8), 256, 0, s, (const float*)a.g, a.n, tt, a.tensor_sumsq);
     ++g_kernel_launches;
     if (a.ctl) { launch_pdl(latch_unscale_kernel, 1, 32, 0, s, a.ctl); ++g_kernel_launches; }
     launch_pdl(step_control_kernel, 1, 32, 0, s, a.tensor_sumsq, tt.n, a.ctl, a.grad_scale, a.growth_steps > 0.f ? a.growth_steps : 2000.f,

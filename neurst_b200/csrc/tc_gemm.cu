@@ -539,8 +539,10 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
         }
       };
-      for (int c = 0; c < C; ++c) { load_w1(c); if (c > 0) load_w2(c - 1); }
-      load_w2(C - 1);
+      // consumption order of the MMA warp: GEMM1 runs two chunks ahead of GEMM2 (see there)
+      load_w1(0);
+      if (C > 1) load_w1(1);
+      for (int c = 0; c < C; ++c) { if (c + 2 < C) load_w1(c + 2); load_w2(c); }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -593,8 +595,12 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       };
       ptx::mbar_wait(x_full, 0);
       ptx::tc_fence_after();
-      for (int c = 0; c < C; ++c) { gemm1(c); if (c > 0) gemm2(c - 1); }
-      gemm2(C - 1);
+      // GEMM1 of chunk c + 2 is issued BEFORE GEMM2 of chunk c: GEMM2(c) has to wait for the epilogue warps to turn the hidden
+      // accumulator of chunk c into its smem operand, and the tensor pipe spends that time on the next-but-one GEMM1 (its TMEM
+      // buffer (c & 1) is free as soon as the epilogue of chunk c has loaded its registers)
+      gemm1(0);
+      if (C > 1) gemm1(1);
+      for (int c = 0; c < C; ++c) { if (c + 2 < C) gemm1(c + 2); gemm2(c); }
       ptx::mma_commit(out_full);
     }
   } else {

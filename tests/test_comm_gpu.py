@@ -1,0 +1,70 @@
+"""In-library NCCL gradient aggregation (b200st_comm_* / b200st_train_step): two ranks on two GPUs.  Each rank computes
+its local gradients twice with the same dropout seed — once without the all-reduce, once with the bucketed, overlapped
+all-reduce inside the backward pass — and the reduced arena must equal the sum of the ranks' local arenas (gathered
+through torch.distributed).  Also the eager vs CUDA-graph step and the rank-0 parameter broadcast."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from neurst_b200.trainer import build_speech_transformer_trainer, synthetic_batch
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        tr, _ = build_speech_transformer_trainer("speech_transformer_s", vocab_size=96, precision="fp16", label_smoothing=0.1,
+                                                 seed=5 + rank, use_cuda_graph=False)       # different init per rank
+        rt = tr.rt
+        assert tr.lib_comm and rt.comm_stats()["world"] == world
+        p0 = rt.params.clone()
+        g0 = [torch.empty_like(p0) for _ in range(world)]
+        dist.all_gather(g0, p0)
+        assert torch.equal(g0[0], p0), "broadcast_parameters: every rank must hold rank 0's parameters"
+        batch = synthetic_batch(4, 160, 12, 96, seed=100 + rank, device="cuda")
+        b = dict(batch); b.update(training=True, seed=77 * world + rank, want_logits=False)
+        rt.ensure_grads().zero_()
+        rt.run(b, backward=True)
+        local = rt.grads.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        expect = sum(gathered)
+        rt.grads.zero_()
+        b2 = dict(b); b2["allreduce"] = True
+        rt.run(b2, backward=True)
+        torch.cuda.synchronize()
+        st = rt.comm_stats()
+        err = float((rt.grads - expect).norm() / expect.norm())
+        # graph-captured step with the all-reduce inside the graph
+        from neurst_b200.runtime import GraphedTrainStep
+        gs = GraphedTrainStep(rt, 4, 160, 12, allreduce=True).capture()
+        rt.grads.zero_()
+        gs(batch, 77 * world + rank)
+        torch.cuda.synchronize()
+        err_g = float((rt.grads - expect).norm() / expect.norm())
+        q.put((rank, err, err_g, st["reduced_elems"], st["calls"], rt.numel))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_bucketed_allreduce_inside_the_library_two_ranks():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(120)
+    for rank, err, err_g, n_red, calls, numel in res:
+        assert err < 1e-5 and err_g < 1e-5, (rank, err, err_g)        # fp32 sums: only the summation order differs
+        assert n_red == numel and calls == 4, (n_red, numel, calls)   # whole arena, in 4 buckets
