@@ -335,8 +335,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+constexpr int kBwdThreads = 64 + 512;     // TMA warp + MMA warp + 16 compute warps (4 per TMEM lane quadrant, 32 key columns each)
+__device__ __forceinline__ void bwd_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 template <bool CAUSAL, int DT>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -368,8 +371,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV); ptx::prefetch_tensormap(&tmdO);
     ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(qdo_full(s), 1); ptx::mbar_init(qdo_empty(s), 1); }
-    ptx::mbar_init(sdp_full, 1); ptx::mbar_init(pds_full, 8);
-    ptx::mbar_init(dq_full, 1); ptx::mbar_init(dq_empty, 8);
+    ptx::mbar_init(sdp_full, 1); ptx::mbar_init(pds_full, 16);
+    ptx::mbar_init(dq_full, 1); ptx::mbar_init(dq_empty, 16);
     ptx::fence_mbar_init();
   }
   if (warp == 1) { ptx::tmem_alloc_n<512>(tmem_slot); ptx::tmem_relinquish(); }
@@ -441,11 +444,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // 8 compute warps: thread = (row of the tile, half of the columns); no cross-warp reductions are needed in backward.
+    // 16 compute warps: thread = (row of the tile, quarter of the key columns) — four warps per scheduler hide the TMEM /
+    // shared-memory latencies of the per-pair softmax recompute; no cross-warp reductions are needed in backward.
     // Branch-free element math as in the forward kernel (bias table in smem, one FFMA + one MUFU per probability); the
     // dropout scale is folded into dS (FFMA) and into the dV epilogue.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int quarter = (warp - 2) >> 2;             // 0..3: key columns [32 * quarter, +32)
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t thresh = dropout_thresh16(p.drop.p);
@@ -459,22 +463,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int k = jb * BKV + t;
         btab[t] = (k < p.Tk) ? (bias_row ? __ldg(bias_row + k) * kLog2e : 0.f) : -INFINITY;
       }
-      softmax_bar();
+      bwd_bar();
     }
-    const int kbase = jb * BKV + half * 64;
-    const float4* bt4 = reinterpret_cast<const float4*>(btab + half * 64);
+    const int c0 = quarter * 32;
+    const int kbase64 = jb * BKV + (quarter >> 1) * 64;      // keep-bits come as aligned 64-key words
+    const float4* bt4 = reinterpret_cast<const float4*>(btab + c0);
     // per-tile row scalars (D = rowsum(dO * O), LSE in the log2 domain: +inf on padding rows => P = 0, keep bits) are
     // prefetched one tile ahead so their global-load latency hides behind the previous tile's math
-    auto load_row = [&](int i, float& Dq, float& lse2, uint32_t (&keep)[2]) {
+    auto load_row = [&](int i, float& Dq, float& lse2, uint32_t& keep) {
       const int q = i * BQ + row;
       const bool qv = q < p.Tq;
       const int64_t row_g = ((int64_t)b * p.H + h) * p.Tq + q;
       Dq = qv ? __ldg(p.dvec + row_g) : 0.f;
       lse2 = qv ? __ldg(p.lse + row_g) * kLog2e : INFINITY;
-      load_keep64(p.drop, qv, row_g * p.Tkp, kbase, p.Tkp, thresh, keep);
+      uint32_t k2[2];
+      load_keep64(p.drop, qv, row_g * p.Tkp, kbase64, p.Tkp, thresh, k2);
+      keep = k2[quarter & 1];
     };
     float Dq, lse2, Dq_n = 0.f, lse2_n = INFINITY;
-    uint32_t keep[2], keep_n[2] = {0xffffffffu, 0xffffffffu};
+    uint32_t keep, keep_n = 0xffffffffu;
     load_row(0, Dq, lse2, keep);
     for (int i = 0; i < nq; ++i) {
       const int q = i * BQ + row;
@@ -484,25 +491,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       ptx::mbar_wait(sdp_full, (uint32_t)i & 1u);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;
+      {
         uint32_t rs[32], rp[32];
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
         ptx::tmem_ld_32x32b_x32(tdP + lane_addr + c0, rp);
         ptx::tmem_ld_wait();
-        const uint32_t kw = keep[cc];
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const float4 b0 = bt4[cc * 8 + g8 * 2], b1 = bt4[cc * 8 + g8 * 2 + 1];
+          const float4 b0 = bt4[g8 * 2], b1 = bt4[g8 * 2 + 1];
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          const uint32_t kb = kw >> (8 * g8);
+          const uint32_t kb = keep >> (8 * g8);
           float pd[8], ds[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             float x = fmaf(__uint_as_float(rs[g8 * 8 + t]), a2, bb[t]);
-            if (CAUSAL) x = (kbase + cc * 32 + g8 * 8 + t > qlim) ? x + cmask : x;
+            if (CAUSAL) x = (jb * BKV + c0 + g8 * 8 + t > qlim) ? x + cmask : x;
             const float pr = ex2_approx(x - lse2);
             const bool kp = (kb >> t) & 1u;
             const float dpv = kp ? __uint_as_float(rp[g8 * 8 + t]) : 0.f;
@@ -518,18 +522,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pds_full);
-      // ---- dQ tile (this half's 32 columns) -> fp32 reduction across kv blocks ----
+      // ---- dQ tile (this warp's 16 columns) -> fp32 reduction across kv blocks ----
       ptx::mbar_wait(dq_full, (uint32_t)i & 1u);
       ptx::tc_fence_after();
-      float* dq_row = p.dq_acc + ((int64_t)b * p.Tq + q) * p.dq_ld + h * DH + half * 32;
+      float* dq_row = p.dq_acc + ((int64_t)b * p.Tq + q) * p.dq_ld + h * DH + quarter * 16;
       {
-        uint32_t r[32];
+        uint32_t r[16];
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32(tdQ + lane_addr + half * 32, r);
+        ptx::tmem_ld_32x32b_x16(tdQ + lane_addr + quarter * 16, r);
         ptx::tmem_ld_wait();
         if (qv) {
 #pragma unroll
-          for (int t = 0; t < 32; t += 4)
+          for (int t = 0; t < 16; t += 4)
             red_add_v4(dq_row + t, __uint_as_float(r[t]) * p.alpha, __uint_as_float(r[t + 1]) * p.alpha,
                        __uint_as_float(r[t + 2]) * p.alpha, __uint_as_float(r[t + 3]) * p.alpha);
         }
@@ -537,21 +541,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(dq_empty);
-      Dq = Dq_n; lse2 = lse2_n; keep[0] = keep_n[0]; keep[1] = keep_n[1];
+      Dq = Dq_n; lse2 = lse2_n; keep = keep_n;
     }
-    // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them); 32 columns per half ----
+    // ---- dV, dK of this kv block (all MMAs retired: the last dq_full commit covers them); 16 columns per warp ----
     const int kk = jb * BKV + row;
-    uint16_t* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH + half * 32;
-    uint16_t* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH + half * 32;
+    uint16_t* dv_row = p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH + quarter * 16;
+    uint16_t* dk_row = p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH + quarter * 16;
     {
-      uint32_t rv[32], rk[32];
+      uint32_t rv[16], rk[16];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(tdV + lane_addr + half * 32, rv);
-      ptx::tmem_ld_32x32b_x32(tdK + lane_addr + half * 32, rk);
+      ptx::tmem_ld_32x32b_x16(tdV + lane_addr + quarter * 16, rv);
+      ptx::tmem_ld_32x32b_x16(tdK + lane_addr + quarter * 16, rk);
       ptx::tmem_ld_wait();
       if (kk < p.Tk) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 8) {
+        for (int t = 0; t < 16; t += 8) {
           uint4 a, c;
           a.x = pack_bf16(__uint_as_float(rv[t]) * dscale, __uint_as_float(rv[t + 1]) * dscale);
           a.y = pack_bf16(__uint_as_float(rv[t + 2]) * dscale, __uint_as_float(rv[t + 3]) * dscale);
@@ -712,7 +716,7 @@ int attention_bwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int6
   dim3 grid((Tk + BKV - 1) / BKV, H, B);
   auto kern = causal ? (dt == F16 ? attn_bwd_kernel<true, F16> : attn_bwd_kernel<true, BF16>)
                      : (dt == F16 ? attn_bwd_kernel<false, F16> : attn_bwd_kernel<false, BF16>);
-  launch_pdl(kern, grid, 320, kBwdSmem, s, tq, tk, tv, tdo, p);
+  launch_pdl(kern, grid, kBwdThreads, kBwdSmem, s, tq, tk, tv, tdo, p);
   B200ST_LAUNCH_CHECK();
   const int64_t n8 = rows * (H * DH / 8);
   int64_t g = (n8 + 255) / 256;

@@ -993,6 +993,12 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
     g.A = GemmOperand{dlogits, c.adt, 0, V, 0, 0};
     g.B = c.W("trg.emb", 1, d);
     g.C = d_dec; g.c_dtype = F32; g.ldc = d;
+    if (is16(c.adt)) {
+      // K = V = 8192 against only (B*L / 128) x (d / 64) output tiles: split-K with fp32 reduce-add into a zeroed buffer
+      RUN(cudaMemsetAsync(d_dec, 0, sizeof(float) * (size_t)Md * d, c.st) == cudaSuccess ? 0 : 1);
+      g.epi.accumulate = 1;
+      g.splitk = 0;
+    }
     RUN(gemm(g, c.st));
   }
   float* dy = c.f32((int64_t)Md * d);

@@ -113,3 +113,18 @@ def test_noam_matches_oracle():
     kw = dict(dmodel=256, warmup_steps=25000, initial_factor=3.5, end_factor=1.5, start_decay_at=50000, decay_steps=50000)
     for step in (0, 10, 24999, 25000, 60000, 99999, 200000):
         assert abs(noam_learning_rate(step, **kw) - R.noam_lr(step, **kw)) < 1e-12
+
+
+def test_throughput_meter_lines_follow_the_reference_format():
+    """MetricReductionCallback's `<metric>_per_step` / `<metric>_per_sec` lines (neurst/training/callbacks.py:209-245)."""
+    from neurst_b200.trainer import ThroughputMeter
+    lines = []
+    m = ThroughputMeter(summary_steps=2, world=4, logger=lines.append)
+    batch = dict(src=torch.zeros(8, 100, 80, 1), trg_input=torch.zeros(8, 12, dtype=torch.long),
+                 src_length=torch.full((8,), 90), trg_length=torch.full((8,), 10))
+    m.add(batch); assert m.step_end(1, torch.tensor(3.0), 1e-3) is None
+    m.add(batch)
+    out = m.step_end(2, torch.tensor(2.5), 1e-3)
+    assert out["src_tokens_per_step"] == 8 * 100 * 4 and out["src_real_tokens_per_step"] == 8 * 90 * 4
+    assert out["trg_tokens_per_step"] == 8 * 12 * 4 and out["samples_per_step"] == 32
+    assert out["src_tokens_per_sec"] > 0 and lines[0].startswith("Update 2\tTrainingLoss=2.50\tSpeed")
