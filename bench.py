@@ -475,7 +475,10 @@ def run_gpu(args):
                                                                    "length buckets %s (T,B,L), src_length~U(0.6T,T)" % (shapes,)),
                    "global_batch_frames": frames, "real_frames_per_sec": real_frames / (ms_step * 1e-3), "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph, "kernels_per_step": int(launches_per_step),
                    "l2_policy": "inputs+activations per step (~4 GB) exceed the 126 MB L2; 4 rotating input batches",
-                   "loss_last_step": loss_val},
+                   "loss_last_step": loss_val,
+                   "loss_scale_state": (dict(zip(("scale", "finite_steps_in_a_row", "last_step_skipped", "skipped_steps", "applied_steps",
+                                                  "global_grad_norm"), [float(x) for x in trainer.rt.loss_scale_state[:6].tolist()]))
+                                        if getattr(trainer.rt, "loss_scale_state", None) is not None else None)},
         "clocks": clocks,
         "e2e": {"value": frames / (ms_e2e / args.steps * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

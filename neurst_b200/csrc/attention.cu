@@ -33,6 +33,7 @@ struct AttnParams {
   int B, H, Tq, Tk, Tkp;
   float alpha;                 // dh^-0.5
   const float* bias;           // [B, Tk] additive or null
+  const int32_t* kv_len;       // [B] or null: keys >= kv_len[b] are padding (bias -1e9): their key blocks are skipped
   int causal;
   DropoutSpec drop;
   uint16_t* ctx; int64_t ctx_ld;          // [B*Tq, H*64], 16-bit type DT (bf16 or fp16)
@@ -115,14 +116,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int nblk = (p.Tk + BKV - 1) / BKV;
+  const int nblk_all = (p.Tk + BKV - 1) / BKV;       // sizes the bias table (launch-time shared memory)
+  // key blocks that hold at least one non-padded key (kv_len is written at the very start of the step, many kernels back:
+  // complete and visible before this kernel's predecessor could start, so it may be read ahead of griddepcontrol.wait)
+  const int nblk = p.kv_len ? max(1, min(nblk_all, (__ldg(p.kv_len + blockIdx.z) + BKV - 1) / BKV)) : nblk_all;
   const uint32_t sQ = base;                          // 16 KB
   const uint32_t sK = sQ + kTile16K;                 // 2 x 16 KB
   const uint32_t sV = sK + 2 * kTile16K;             // 16 KB
   const uint32_t sP = sV + kTile16K;                 // 32 KB
   const uint32_t sX = sP + 2 * kTile16K;             // exchange: max [2][2][128] + sum [2][128] floats = 3 KB
   const uint32_t sB = sX + 3072;                     // key bias * log2(e), [nblk * 128] floats
-  const uint32_t bars = sB + (uint32_t)nblk * 512u;
+  const uint32_t bars = sB + (uint32_t)nblk_all * 512u;
   const uint32_t q_full = bars, v_full = bars + 8, v_empty = bars + 16, s_full = bars + 24, s_empty = bars + 32,
                  p_full = bars + 40, p_empty = bars + 48, o_ready = bars + 56, tmem_slot = bars + 64;
   auto k_full = [&](int s2) { return bars + 72u + 8u * s2; };
@@ -366,6 +370,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nq = (p.Tq + BQ - 1) / BQ;
+  if (p.kv_len && jb > 0 && jb * BKV >= __ldg(p.kv_len + b)) {
+    // every key of this block is padding: P = 0 exactly, so dK = dV = 0 and the block adds nothing to dQ
+    pdl_wait();
+    pdl_trigger();
+    for (int i = threadIdx.x; i < BKV * (DH / 8); i += blockDim.x) {
+      const int r = i / (DH / 8), c8 = (i % (DH / 8)) * 8, kk = jb * BKV + r;
+      if (kk < p.Tk) {
+        *reinterpret_cast<uint4*>(p.dv + ((int64_t)b * p.Tk + kk) * p.dv_ld + h * DH + c8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(p.dk + ((int64_t)b * p.Tk + kk) * p.dk_ld + h * DH + c8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    return;
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV); ptx::prefetch_tensormap(&tmdO);
@@ -636,7 +653,7 @@ constexpr size_t kFwdSmemFixed = 1024 + (size_t)(1 + 2 + 1 + 2) * kTile16K + 307
 // q/k/v: bf16 views [B*T, ld] with head h at columns [h*64, h*64+64)
 int attention_fwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
                         int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
-                        cudaStream_t s) {
+                        cudaStream_t s, const int32_t* kv_len) {
   B200ST_CHECK(Tq > 0 && Tk > 0 && B > 0 && H > 0, "empty attention");
   B200ST_CHECK(B <= 65535 && H <= 65535, "attention grid too large");
   B200ST_CHECK(is16(dt), "fused attention needs a 16-bit operand type");
@@ -647,7 +664,7 @@ int attention_fwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int6
   AttnParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.Tkp = (Tk + 7) / 8 * 8;
   p.alpha = 0.125f;                     // 64^-0.5 (multi_head_attention.py:203)
-  p.bias = bias; p.causal = causal; p.drop = drop;
+  p.bias = bias; p.causal = causal; p.drop = drop; p.kv_len = kv_len;
   p.ctx = reinterpret_cast<uint16_t*>(ctx); p.ctx_ld = ctx_ld; p.lse = lse;
   B200ST_CHECK((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && ctx_ld % 8 == 0, "ctx must be 16-byte aligned");
   const size_t smem = kFwdSmemFixed + (size_t)((Tk + BKV - 1) / BKV) * 512;
@@ -672,7 +689,7 @@ int attention_fwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int6
 int attention_bwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
                         int64_t ctx_ld, const void* dctx, int64_t dctx_ld, const float* lse, int B, int H, int Tq, int Tk,
                         const float* bias, int causal, DropoutSpec drop, float* dq_scratch, void* dq, int64_t dq_ld, void* dk,
-                        int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s) {
+                        int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s, const int32_t* kv_len) {
   B200ST_CHECK(Tq > 0 && Tk > 0 && B > 0 && H > 0 && B <= 65535 && H <= 65535, "bad attention shape");
   B200ST_CHECK(is16(dt), "fused attention needs a 16-bit operand type");
   CUtensorMap tq, tk, tv, tdo;
@@ -683,7 +700,7 @@ int attention_bwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int6
   AttnParams p{};
   p.B = B; p.H = H; p.Tq = Tq; p.Tk = Tk; p.Tkp = (Tk + 7) / 8 * 8;
   p.alpha = 0.125f;
-  p.bias = bias; p.causal = causal; p.drop = drop;
+  p.bias = bias; p.causal = causal; p.drop = drop; p.kv_len = kv_len;
   p.ctx = reinterpret_cast<uint16_t*>(const_cast<void*>(ctx)); p.ctx_ld = ctx_ld;
   p.lse = const_cast<float*>(lse);
   p.dctx = reinterpret_cast<const uint16_t*>(dctx); p.dctx_ld = dctx_ld;

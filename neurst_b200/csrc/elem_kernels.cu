@@ -799,7 +799,8 @@ int embed_bwd(const int64_t* ids, const float* dx, float* dE, int B, int L, int 
   return 0;
 }
 
-__global__ void length_to_bias_kernel(const int64_t* __restrict__ lengths, float* __restrict__ bias, int B, int T, int n_halvings) {
+__global__ void length_to_bias_kernel(const int64_t* __restrict__ lengths, float* __restrict__ bias, int B, int T, int n_halvings,
+                                      int32_t* __restrict__ klen) {
   pdl_wait();
   pdl_trigger();
   const int64_t n = (int64_t)B * T;
@@ -808,11 +809,12 @@ __global__ void length_to_bias_kernel(const int64_t* __restrict__ lengths, float
     int64_t len = lengths[b];
     for (int h = 0; h < n_halvings; ++h) len = (len + 1) / 2;
     bias[i] = t >= len ? kFloatMin : 0.f;
+    if (klen && t == 0) klen[b] = (int32_t)(len < 1 ? T : (len > T ? T : len));     // number of leading non-padded keys
   }
 }
-int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s) {
+int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s, int32_t* klen) {
   if ((int64_t)B * T == 0) return 0;
-  launch_pdl(length_to_bias_kernel, grid_for((int64_t)B * T, 256), 256, 0, s, lengths, bias, B, T, n_halvings);
+  launch_pdl(length_to_bias_kernel, grid_for((int64_t)B * T, 256), 256, 0, s, lengths, bias, B, T, n_halvings, klen);
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

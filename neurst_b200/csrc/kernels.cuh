@@ -52,7 +52,8 @@ int embed_bwd(const int64_t* ids, const float* dx, float* dE, int B, int L, int 
 
 // bias[b,k] = (k >= len[b]) ? -1e9 : 0   with len from `lengths` after `n_conv` ceil-halvings
 // (speech_transformer.py:179-189, layer_utils.py:19-32)
-int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s);
+// klen (optional): int32 [B] = number of leading non-padded keys (the fused attention skips key blocks beyond it)
+int length_to_bias(const int64_t* lengths, float* bias, int B, int T, int n_halvings, cudaStream_t s, int32_t* klen = nullptr);
 int padding_to_bias(const float* padding, float* bias, int64_t n, cudaStream_t s);
 
 // label-smoothed CE forward (+ backward when dlogits != null) (label_smoothed_cross_entropy.py:94-157,46-53)
@@ -104,13 +105,15 @@ int fill_f32(float* x, float v, int64_t n, cudaStream_t s);
 // ---- fused attention (16-bit operand type `dt` = BF16 or F16, head dim 64): tcgen05 QK^T / PV with on-chip online softmax (attention.cu) ----
 // q/k/v/ctx/dctx/dq/dk/dv: bf16 views [B*T, ld], head h at columns [h*64, h*64+64); bias fp32 [B,Tk] or null;
 // lse fp32 [B,H,Tq] (written by forward, read by backward); dq_scratch fp32 [B*Tq, H*64] followed by [B*H*Tq] floats (rowsum(dO*O)).
+// kv_len (optional, int32 [B]): keys >= kv_len[b] all carry the -1e9 padding bias — their probabilities are exactly 0 in
+// fp32, so whole key blocks beyond it are skipped (bit-identical result; ragged batches of cfg-4)
 int attention_fwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, int B, int H,
                         int Tq, int Tk, const float* bias, int causal, DropoutSpec drop, void* ctx, int64_t ctx_ld, float* lse,
-                        cudaStream_t s);
+                        cudaStream_t s, const int32_t* kv_len = nullptr);
 int attention_bwd_fused(int dt, const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, const void* ctx,
                         int64_t ctx_ld, const void* dctx, int64_t dctx_ld, const float* lse, int B, int H, int Tq, int Tk,
                         const float* bias, int causal, DropoutSpec drop, float* dq_scratch, void* dq, int64_t dq_ld, void* dk,
-                        int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s);
+                        int64_t dk_ld, void* dv, int64_t dv_ld, cudaStream_t s, const int32_t* kv_len = nullptr);
 
 // ---- conv front-end (audio_modalities.py:84-109) ----
 // y1 = relu(LN(conv3x3s2(src) + b)); src fp32 [B,T,F,Cin]; w fp32 HWIO [3,3,Cin,C]; y1 (dtype) [B,T1,F1,C]

@@ -227,6 +227,11 @@ struct Ctx {
     sync_hi = lo;
     return rc;
   }
+  // ragged batches: number of leading non-padded encoder positions per utterance; applies to attention calls whose key
+  // bias is the encoder padding bias (encoder self-attention, decoder cross-attention)
+  const float* klen_bias = nullptr;
+  const int32_t* klen = nullptr;
+  const int32_t* klen_for(const float* bias) const { return (bias && bias == klen_bias) ? klen : nullptr; }
   bool dry;        // planning pass: allocate only, launch nothing
   bool training;
   uint64_t seed;
@@ -367,7 +372,8 @@ static bool use_fused_attention(const Ctx& c, const AttnDims& a) {
 static int attention_fwd(Ctx& c, const AttnDims& a, View q, View k, View v, const float* bias, int causal, DropoutSpec drop,
                          float* S, void* p_pre, void* p_drop, void* ctx, float* lse) {
   if (use_fused_attention(c, a)) {
-    RUN(attention_fwd_fused(c.adt, q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, a.B, a.H, a.Tq, a.Tk, bias, causal, drop, ctx, a.units, lse, c.st));
+    RUN(attention_fwd_fused(c.adt, q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, a.B, a.H, a.Tq, a.Tk, bias, causal, drop, ctx, a.units, lse, c.st,
+                            c.klen_for(bias)));
     return 0;
   }
   const int dh = a.units / a.H, Tkp = round8(a.Tk);
@@ -394,7 +400,7 @@ static int attention_bwd(Ctx& c, const AttnDims& a, View q, View k, View v, cons
                          const float* lse, const float* bias, int causal, float* dq32) {
   if (use_fused_attention(c, a)) {
     RUN(attention_bwd_fused(c.adt, q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, ctx, a.units, dctx, a.units, lse, a.B, a.H, a.Tq, a.Tk, bias, causal,
-                            drop, dq32, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, c.st));
+                            drop, dq32, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, c.st, c.klen_for(bias)));
     return 0;
   }
   const int dh = a.units / a.H, Tkp = round8(a.Tk);
@@ -914,7 +920,9 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   FrontSave fs;
   if (speech) {
     B200ST_CHECK(c.dry || (b.src && b.src_length), "speech model needs src and src_length");
-    RUN(length_to_bias(b.src_length, enc_bias, B, Ts, 2, c.st));
+    int32_t* klen = reinterpret_cast<int32_t*>(c.f32(B));
+    RUN(length_to_bias(b.src_length, enc_bias, B, Ts, 2, c.st, klen));
+    c.klen_bias = enc_bias; c.klen = klen;
     B200ST_TRY(speech_front_fwd(c, b.src, B, b.T, x0, fs));
   } else {
     B200ST_CHECK(c.dry || (b.src_ids && b.src_padding), "text model needs src ids and src_padding");
