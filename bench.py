@@ -450,6 +450,7 @@ def run_gpu(args):
         if cpu is None:
             cpu = {"value": None, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                    "sample": "oracle sample exceeded its time budget on this host (loaded CPU)"}
+    trainer.close()              # NCCL communicator of the library: closed on every rank at the same point
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

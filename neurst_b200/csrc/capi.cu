@@ -132,6 +132,11 @@ int b200st_comm_init(b200st_handle h, const char* id128, int32_t nranks, int32_t
   if (h->m.sync) { comm_destroy(h->m.sync); h->m.sync = nullptr; }
   return comm_init(&h->m.sync, id128, nranks, rank);
 }
+int b200st_comm_destroy(b200st_handle h) {
+  if (!h) B200ST_FAIL("null handle");
+  if (h->m.sync) { comm_destroy(h->m.sync); h->m.sync = nullptr; }
+  return 0;
+}
 int b200st_comm_stats(b200st_handle h, int64_t* reduced_elems, int32_t* calls, int32_t* world) {
   if (!h) B200ST_FAIL("null handle");
   if (reduced_elems) *reduced_elems = comm_reduced_elems(h->m.sync);
@@ -154,7 +159,8 @@ int b200st_train_step(b200st_handle h, const b200st_buffers* buf, const b200st_b
   return 0;
 }
 int b200st_destroy(b200st_handle h) {
-  if (h && h->m.sync) { comm_destroy(h->m.sync); h->m.sync = nullptr; }
+  // a still-open communicator is left to the process teardown: ncclCommDestroy from a destructor that runs while the other
+  // ranks (or the CUDA context) are already gone can block — b200st_comm_destroy is the explicit, collective-ordered exit
   delete h;
   return 0;
 }

@@ -154,6 +154,13 @@ class Runtime:
         self.comm_world = world
         return self
 
+    def comm_close(self):
+        """Destroys the library's NCCL communicator (every rank, before torch.distributed.destroy_process_group)."""
+        if getattr(self, "comm_world", 0):
+            torch.cuda.synchronize(self.device)
+            L.check(self.lib.b200st_comm_destroy(self.handle))
+            self.comm_world = 0
+
     def comm_broadcast_parameters(self, root=0):
         L.check(self.lib.b200st_comm_broadcast(self.handle, _ptr(self.params), self.numel, int(root), L._stream()))
         self._shadow_stale = True

@@ -75,6 +75,14 @@ class DataParallelTrainer:
             self.rt.comm_init(self.dist)
         self.meter = ThroughputMeter(summary_steps, self.world, logger) if summary_steps else None
 
+    def close(self):
+        """Collective-ordered shutdown of the in-library communicator (call on every rank before leaving the job)."""
+        if self.lib_comm:
+            if self.dist:
+                self.dist.barrier()
+            self.rt.comm_close()
+            self.lib_comm = False
+
     def broadcast_parameters(self):
         """rank 0 -> all (hvd BroadcastGlobalVariablesCallback, exps/trainer.py:285)."""
         if self.lib_comm:

@@ -47,7 +47,13 @@ def _worker(rank, world, port, q):
         gs(batch, 77 * world + rank)
         torch.cuda.synchronize()
         err_g = float((rt.grads - expect).norm() / expect.norm())
-        q.put((rank, err, err_g, st["reduced_elems"], st["calls"], rt.numel))
+        # per-bucket error and the run-to-run noise floor of the local gradients (same batch, same seed, no all-reduce)
+        rt.grads.zero_()
+        rt.run(b, backward=True)
+        torch.cuda.synchronize()
+        noise = float((rt.grads - local).norm() / local.norm())
+        q.put((rank, err, err_g, st["reduced_elems"], st["calls"], rt.numel, noise))
+        tr.close()
     finally:
         dist.barrier()
         dist.destroy_process_group()
@@ -65,6 +71,9 @@ def test_bucketed_allreduce_inside_the_library_two_ranks():
     res = [q.get(timeout=600) for _ in range(2)]
     for p in procs:
         p.join(120)
-    for rank, err, err_g, n_red, calls, numel in res:
-        assert err < 1e-5 and err_g < 1e-5, (rank, err, err_g)        # fp32 sums: only the summation order differs
+    for rank, err, err_g, n_red, calls, numel, noise in res:
+        print("rank %d: reduced-vs-sum rel err eager %.2e graph %.2e, run-to-run noise of the local gradients %.2e" % (rank, err, err_g, noise))
+        # the reduced arena is the sum of two independently recomputed local arenas: the bound is the run-to-run noise of the
+        # backward pass itself (fp32 atomics order -> 1-ulp flips of 16-bit intermediates), not of the reduction
+        assert err < max(1e-5, 4 * noise) and err_g < max(1e-5, 4 * noise), (rank, err, err_g, noise)
         assert n_red == numel and calls == 4, (n_red, numel, calls)   # whole arena, in 4 buckets
