@@ -11,6 +11,7 @@
 
 #include <dlfcn.h>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200st {
 
@@ -21,6 +22,7 @@ typedef int ncclResult_t;
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, void*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -41,6 +43,7 @@ NcclApi& nccl() {
   if (!h) return api;
   api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
   api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(h, "ncclBroadcast"));
@@ -56,9 +59,20 @@ NcclApi& nccl() {
   } while (0)
 }  // namespace
 
+// ncclConfig_t as of NCCL 2.27 (nccl.h: ncclConfig_v22700); newer libraries accept older sizes / versions
+struct NcclConfig227 {
+  size_t size; unsigned int magic; unsigned int version;
+  int blocking, cgaClusterSize, minCTAs, maxCTAs;
+  const char* netName;
+  int splitShare, trafficClass;
+  const char* commName;
+  int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs;
+};
+
 struct GradSync {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  int max_ctas = 0;               // CTAs (= SMs) the communicator may occupy; 0 = NCCL's default
   cudaStream_t cs = nullptr;
   cudaEvent_t ready = nullptr, done = nullptr;
   int64_t reduced_elems = 0;      // of the current backward pass (tests / bench)
@@ -80,7 +94,24 @@ int comm_init(GradSync** out, const char* id128, int nranks, int rank) {
   g->nranks = nranks; g->rank = rank;
   ncclUniqueId id;
   std::memcpy(id.internal, id128, 128);
-  ncclResult_t r = nccl().CommInitRank(&g->comm, nranks, id, rank);
+  // The all-reduces run UNDER the backward kernels: cap the SMs NCCL may take (its kernels hold an SM for the whole
+  // transfer, and the persistent GEMM grids are sized to the SMs that are left, see comm_reserved_sms)
+  const char* env = getenv("B200ST_NCCL_MAX_CTAS");
+  g->max_ctas = env ? atoi(env) : 8;
+  ncclResult_t r = 1;
+  if (g->max_ctas > 0 && nccl().CommInitRankConfig) {
+    NcclConfig227 cfg;
+    const int undef = (int)0x80000000;
+    cfg.size = sizeof(NcclConfig227); cfg.magic = 0xcafebeefu; cfg.version = 22703u;
+    cfg.blocking = undef; cfg.cgaClusterSize = undef; cfg.minCTAs = undef; cfg.maxCTAs = g->max_ctas;
+    cfg.netName = nullptr; cfg.splitShare = undef; cfg.trafficClass = undef; cfg.commName = nullptr;
+    cfg.collnetEnable = undef; cfg.CTAPolicy = undef; cfg.shrinkShare = undef; cfg.nvlsCTAs = undef;
+    r = nccl().CommInitRankConfig(&g->comm, nranks, id, rank, &cfg);
+    if (r != 0) g->max_ctas = 0;
+  } else {
+    g->max_ctas = 0;
+  }
+  if (r != 0) r = nccl().CommInitRank(&g->comm, nranks, id, rank);
   if (r != 0) { delete g; B200ST_FAIL(std::string("ncclCommInitRank: ") + nccl().GetErrorString(r)); }
   if (cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming) != cudaSuccess ||
@@ -103,6 +134,7 @@ void comm_destroy(GradSync* g) {
 }
 
 int comm_world(const GradSync* g) { return g ? g->nranks : 1; }
+int comm_reserved_sms(const GradSync* g) { return g ? g->max_ctas : 0; }
 int64_t comm_reduced_elems(const GradSync* g) { return g ? g->reduced_elems : 0; }
 int comm_calls(const GradSync* g) { return g ? g->calls : 0; }
 void comm_begin_step(GradSync* g) { if (g) { g->reduced_elems = 0; g->calls = 0; } }

@@ -89,6 +89,7 @@ struct TcDebug {
   int force_stages; // 0 = auto
   int max_ctas;     // 0 = #SMs
   int one_cta_per_sm; // 1 = disable the 2-CTAs-per-SM mode of the BN <= 128 variants
+  int reserve_sms;    // SMs left to concurrent communication kernels (set by the model while gradient all-reduces overlap)
 };
 TcDebug& tc_debug();
 int64_t tc_launch_count();

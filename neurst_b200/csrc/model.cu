@@ -976,6 +976,9 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
     c.sync = c.m.sync;
     c.sync_hi = c.m.arena_numel;
     comm_begin_step(c.sync);
+    // the persistent GEMM grids assign tiles statically to `gridDim.x` CTAs: size them to the SMs NCCL leaves free, or the
+    // CTAs that find no SM run as a second wave after the others have finished
+    if (comm_reserved_sms(c.sync) > 0) tc_debug().reserve_sms = comm_reserved_sms(c.sync);
   }
   // reverse-arena-order buckets only when no tensor receives gradient later than its bucket (text models may tie the
   // source and target embeddings: one all-reduce at the end)
@@ -1029,6 +1032,7 @@ static int model_run(Ctx& c, const Batch& b, bool backward) {
   }
   c.join_side();        // the optimizer / all-reduce on `st` must see every weight gradient
   if (c.sync) {
+    tc_debug().reserve_sms = 0;
     B200ST_TRY(c.reduce_down_to(""));        // the rest (front-end, or everything when not bucketed)
     B200ST_TRY(comm_join(c.sync, c.st));
   }

@@ -39,6 +39,7 @@ int comm_unique_id(char* out128);
 int comm_init(GradSync** out, const char* id128, int nranks, int rank);
 void comm_destroy(GradSync* g);
 int comm_world(const GradSync* g);
+int comm_reserved_sms(const GradSync* g);    // SMs the communicator's kernels may hold while the backward pass runs
 int64_t comm_reduced_elems(const GradSync* g);
 int comm_calls(const GradSync* g);
 void comm_begin_step(GradSync* g);

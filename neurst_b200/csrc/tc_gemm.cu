@@ -947,7 +947,7 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
     B200ST_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const TcDebug& dbg = tc_debug();
-  const int num_sms = dbg.max_ctas > 0 ? dbg.max_ctas : g_num_sms;
+  const int num_sms = dbg.max_ctas > 0 ? dbg.max_ctas : (dbg.reserve_sms > 0 && dbg.reserve_sms < g_num_sms ? g_num_sms - dbg.reserve_sms : g_num_sms);
 
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.nb1 = g.nb1; p.nb2 = g.nb2;
@@ -1088,7 +1088,8 @@ int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W
   // slices of the hidden dimension: the most CTAs that still fit one wave, with an equal number of chunks per slice
   int splits = 1;
   for (int s2 = 1; s2 <= chunks; ++s2)
-    if (chunks % s2 == 0 && (int64_t)m_tiles * s2 <= g_num_sms) splits = s2;
+    if (chunks % s2 == 0 && (int64_t)m_tiles * s2 <= g_num_sms - tc_debug().reserve_sms) splits = s2;
+  if (getenv("B200ST_MLP_SPLITS")) { const int f = atoi(getenv("B200ST_MLP_SPLITS")); if (f >= 1 && chunks % f == 0) splits = f; }
   MlpParams p{};
   p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
   p.b1 = b1; p.b2 = b2; p.drop_ffn = drop_ffn; p.drop_post = drop_post;
@@ -1126,7 +1127,8 @@ int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* 
   const int m_tiles = ceil_div(M, BM), chunks = ffn / 128;
   int splits = 1;
   for (int s2 = 1; s2 <= chunks; ++s2)
-    if (chunks % s2 == 0 && (int64_t)m_tiles * s2 <= g_num_sms) splits = s2;
+    if (chunks % s2 == 0 && (int64_t)m_tiles * s2 <= g_num_sms - tc_debug().reserve_sms) splits = s2;
+  if (getenv("B200ST_MLP_SPLITS")) { const int f = atoi(getenv("B200ST_MLP_SPLITS")); if (f >= 1 && chunks % f == 0) splits = f; }
   MlpParams p{};
   p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
   p.b1 = nullptr; p.b2 = nullptr; p.drop_ffn = no_dropout(); p.drop_post = no_dropout();
