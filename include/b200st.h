@@ -176,12 +176,14 @@ typedef struct {
   const int64_t* bos_ids;
   int32_t eos_id, unk_id, min_len, max_steps;
   int64_t* out_ids; int32_t* out_len; float* out_logprob;
-  void* state_words;            /* >= 128 bytes of device memory */
-  int32_t use_graph;
+  void* state_words;            /* >= 256 bytes of device memory */
+  int32_t use_graph;            /* 2: ONE persistent cooperative kernel for the whole search (grid-wide barriers between the
+                                 * phases of a token; falls back to 1 when the grid cannot be co-scheduled); 1: one captured
+                                 * CUDA graph of ~40 kernels replayed per token; 0: eager launches */
 } b200st_greedy_args;
 int b200st_greedy_search(b200st_handle h, const b200st_buffers* buf, const b200st_decode_state* st, const b200st_greedy_args* a,
                          void* stream);
-/* 1 when the last b200st_greedy_search replayed a captured graph, 0 when it launched eagerly (e.g. legacy default stream) */
+/* mode the last b200st_greedy_search actually ran in: 2 persistent kernel, 1 captured graph, 0 eager launches */
 int32_t b200st_greedy_used_graph(void);
 
 /* 16-bit shadow of the parameter arena (tcgen05 operands); shadow_dtype = B200ST_BF16 or B200ST_F16 */

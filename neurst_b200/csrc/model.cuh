@@ -128,7 +128,7 @@ struct GreedyArgs {
   int64_t* out_ids;              // [B, max_steps] device, padded with EOS
   int32_t* out_len;              // [B] device
   float* out_logprob;            // [B] device: accumulated log-probability of the hypothesis
-  void* state_words;             // >= 128 bytes of device memory (ids, finished flags, time)
+  void* state_words;             // >= 256 bytes of device memory (ids, finished flags, time, grid barrier)
   int use_graph;
 };
 int64_t decode_scratch_floats(const Model& m, int B);

@@ -117,7 +117,7 @@ def decoder_step_logits(rt, symbols, cache, time):
 
 
 def greedy_search(rt, inputs, bos_id, eos_id, unk_id=None, maximum_decode_length=256, extra_decode_length=50,
-                  minimum_decode_length=0, enable_unk=False, use_shadow=False, use_graph=True, cache=None):
+                  minimum_decode_length=0, enable_unk=False, use_shadow=False, use_graph=True, cache=None, persistent=True):
     """sequence_beam_search(beam_size=1, top_k=1): returns (hypothesis int64 [B, maximum_decode_length] padded with EOS,
     log-probability [B], decoding length [B]).  `maximum_search_steps` = max(min(T' + extra, maximum), minimum)
     (beam_search.py:357-363)."""
@@ -141,7 +141,9 @@ def greedy_search(rt, inputs, bos_id, eos_id, unk_id=None, maximum_decode_length
     a.unk_id = -1 if (enable_unk or unk_id is None) else int(unk_id)
     a.min_len, a.max_steps = int(minimum_decode_length), int(steps)
     a.out_ids, a.out_len, a.out_logprob = out.data_ptr(), length.data_ptr(), logprob.data_ptr()
-    a.state_words, a.use_graph = words.data_ptr(), int(bool(use_graph))
+    # persistent: the whole search is ONE cooperative kernel (grid barriers between the phases of a token); otherwise one
+    # captured CUDA graph of ~40 kernels is replayed per token (use_graph) or every kernel is launched eagerly
+    a.state_words, a.use_graph = words.data_ptr(), (2 if (persistent and use_graph) else int(bool(use_graph)))
     bufs = _bufs(rt)
     # the library captures the step into a CUDA graph: that needs a real (non-legacy-default) stream
     cur = torch.cuda.current_stream(dev)
@@ -152,8 +154,8 @@ def greedy_search(rt, inputs, bos_id, eos_id, unk_id=None, maximum_decode_length
     with torch.cuda.stream(side):
         L.check(rt.lib.b200st_greedy_search(rt.handle, C.byref(bufs), C.byref(cache.state), C.byref(a), L._stream()))
     cur.wait_stream(side)
-    if use_graph and int(rt.lib.b200st_greedy_used_graph()) != 1:
-        raise L.B200STError("greedy search could not capture its step graph")
+    if use_graph and int(rt.lib.b200st_greedy_used_graph()) < 1:
+        raise L.B200STError("greedy search could neither run its persistent kernel nor capture its step graph")
     if steps < maximum_decode_length:      # padded to the fixed output length with EOS (beam_search.py:428-436)
         out = torch.cat([out, torch.full((B, maximum_decode_length - steps), int(eos_id), dtype=torch.int64, device=dev)], 1)
     return out, logprob, length

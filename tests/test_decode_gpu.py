@@ -26,13 +26,14 @@ def _small_case(seed, precision="fp32"):
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_greedy_token_ids_exact_small(seed, use_graph):
+@pytest.mark.parametrize("use_graph,persistent", [(True, True), (True, False), (False, False)])
+def test_greedy_token_ids_exact_small(seed, use_graph, persistent):
     P, src, lens, rt = _small_case(seed)
     hyp, lp, ln = R.greedy_search(P, SMALL, src, lens, BOS, EOS, UNK, maximum_decode_length=24, extra_decode_length=8)
     ids, logprob, length = D.greedy_search(rt, dict(src=src, src_length=lens), BOS, EOS, UNK, maximum_decode_length=24,
-                                           extra_decode_length=8, use_graph=use_graph)
+                                           extra_decode_length=8, use_graph=use_graph, persistent=persistent)
     torch.cuda.synchronize()
+    assert int(rt.lib.b200st_greedy_used_graph()) == (2 if persistent else int(use_graph))
     assert torch.equal(ids.cpu(), hyp), (ids.cpu().tolist(), hyp.tolist())
     assert torch.equal(length.cpu().long(), ln)
     assert float((logprob.cpu() - lp).abs().max()) < 1e-3
