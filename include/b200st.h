@@ -71,7 +71,10 @@ typedef struct {
   int32_t share_src_trg_embedding;
   int32_t mha_self, mha_din, mha_dmem, mha_dout;
   int32_t with_cross_attention;
-  int32_t disable_fused_attention;   /* tests: materialised attention (GEMM + softmax kernels) in bf16 mode */
+  int32_t disable_fused_attention;   /* tests: materialised attention (GEMM + softmax kernels) and unfused FFN in the 16-bit modes */
+  int32_t deterministic;             /* 1: the hidden-dimension slices of the fused FFN kernel reduce into the output in slice
+                                      * order (ticket per row tile) instead of arrival order: bit-reproducible steps for a few
+                                      * microseconds per FFN launch (default 0: fp32 sums in arrival order) */
 } b200st_config;
 
 int b200st_create(const b200st_config* cfg, b200st_handle* out);   /* host object only; no device memory */

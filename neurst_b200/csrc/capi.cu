@@ -22,7 +22,7 @@ using namespace b200st;
 extern "C" {
 
 const char* b200st_last_error(void) { return g_last_error.c_str(); }
-int b200st_version(void) { return 200; }
+int b200st_version(void) { return 201; }
 int64_t b200st_launch_count(void) { return g_kernel_launches + tc_launch_count(); }
 
 static GemmOperand to_operand(const b200st_operand& o) {
@@ -114,6 +114,7 @@ int b200st_create(const b200st_config* cfg, b200st_handle* out) {
   c.mha_self = cfg->mha_self; c.mha_din = cfg->mha_din; c.mha_dmem = cfg->mha_dmem; c.mha_dout = cfg->mha_dout;
   c.with_cross_attention = cfg->with_cross_attention;
   c.disable_fused_attention = cfg->disable_fused_attention;
+  c.deterministic = cfg->deterministic;
   if (c.model_type < 0 || c.model_type > MODEL_MHA) { delete h; B200ST_FAIL("unknown model_type"); }
   if (c.attention_dropout < 0 || c.attention_dropout >= 1 || c.ffn_dropout < 0 || c.ffn_dropout >= 1 ||
       c.postprocess_dropout < 0 || c.postprocess_dropout >= 1) { delete h; B200ST_FAIL("dropout rates must be in [0,1)"); }

@@ -77,10 +77,11 @@ int gemm(const GemmArgs& g, cudaStream_t stream);
 // (dropout(relu(X W1 + b1)) W2 + b2); the hidden activations are also written to F1 for the backward pass.
 bool fused_mlp_supported(int M, int d, int ffn, int dtype);
 int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W1, const float* b1, const void* W2, const float* b2,
-                  DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream);
+                  DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream, int* tickets = nullptr);
+// tickets (optional): int [ceil(M / 128)], zero before the first use: hidden slices reduce in slice order (deterministic)
 
 int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* W1, const void* W2, const void* F1, float scale,
-                  void* dF1, float* dH, cudaStream_t stream);
+                  void* dF1, float* dH, cudaStream_t stream, int* tickets = nullptr);
 
 // Debug knobs for the descriptor probe (tests only). 0 restores defaults.
 struct TcDebug {

@@ -232,6 +232,16 @@ struct Ctx {
   const float* klen_bias = nullptr;
   const int32_t* klen = nullptr;
   const int32_t* klen_for(const float* bias) const { return (bias && bias == klen_bias) ? klen : nullptr; }
+  // deterministic mode: ticket words of the fused FFN kernel (one array per call, zeroed once, self-resetting)
+  int* tickets = nullptr;
+  int* mlp_tickets(int M) {
+    if (!m.cfg.deterministic) return nullptr;
+    if (!tickets) {
+      tickets = reinterpret_cast<int*>(ar.take(sizeof(int) * 4096));
+      if (!dry && cudaMemsetAsync(tickets, 0, sizeof(int) * 4096, st) != cudaSuccess) launch_failed = true;
+    }
+    return (M + 127) / 128 <= 4096 ? tickets : nullptr;
+  }
   bool dry;        // planning pass: allocate only, launch nothing
   bool training;
   uint64_t seed;
@@ -618,8 +628,9 @@ static int ffn_block_fwd(Ctx& c, const std::string& pre, const float* x_in, floa
                            M, d, 0, x_out, c.st));
     const DropoutSpec d1 = c.drop(cf.ffn_dropout, sv.s_ffn, (int64_t)M * f);
     const DropoutSpec d2 = c.drop(cf.postprocess_dropout, sv.s_post, (int64_t)M * d);
+    int* tk = c.mlp_tickets(M);
     RUN(fused_mlp_fwd(sv.h, c.adt, M, d, f, c.W(pre + ".w1", 1, f).ptr, c.P(pre + ".b1"), c.W(pre + ".w2", 1, d).ptr, c.P(pre + ".b2"),
-                      d1, d2, sv.f1, x_out, c.st));
+                      d1, d2, sv.f1, x_out, c.st, tk));
     return 0;
   }
   RUN(layernorm_fwd(x_in, F32, c.P(pre + ".ln.gamma"), c.P(pre + ".ln.beta"), cf.ln_eps, sv.h, c.adt, nullptr, sv.mean, sv.rstd,
@@ -646,8 +657,9 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
     // data-gradient chain in one kernel: dF1 = (dY W2^T) * relu'/dropout' (written for the W1 weight gradient), dh = dF1 W1^T
     const DropoutSpec fd = c.drop(cf.ffn_dropout, sv.s_ffn);
     RUN(cudaMemsetAsync(sc.dh, 0, sizeof(float) * (size_t)M * d, c.st) == cudaSuccess ? 0 : 1);
+    int* tk = c.mlp_tickets(M);
     RUN(fused_mlp_bwd(sc.dY, c.adt, M, d, f, c.W(pre + ".w1", 0, f).ptr, c.W(pre + ".w2", 0, d).ptr, sv.f1,
-                      fd.p > 0.f ? fd.scale : 1.f, sc.dF1, sc.dh, c.st));
+                      fd.p > 0.f ? fd.scale : 1.f, sc.dF1, sc.dh, c.st, tk));
     B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dF1, f, M, d, f, pre + ".w1", pre + ".b1"));
     B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
     return 0;

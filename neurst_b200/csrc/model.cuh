@@ -24,6 +24,7 @@ struct Config {
   int mha_self, mha_din, mha_dmem, mha_dout;
   int with_cross_attention;   // decoder stack: 1 (default)
   int disable_fused_attention; // tests: use the materialised (GEMM + softmax) attention path in bf16 mode
+  int deterministic;           // fused FFN: slices reduce in slice order (bit-reproducible)
 };
 
 struct ParamInfo {

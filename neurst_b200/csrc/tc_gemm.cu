@@ -439,6 +439,7 @@ struct MlpParams {
   int relu;
   float alpha;
   const void* mask_src; int64_t mask_ld;
+  int* tickets;                // deterministic mode: [m_tiles] zero-initialised; slice s adds after slices < s (self-resetting)
 };
 constexpr int kMlpStages = 3;
 constexpr uint32_t kMlpStageBytes = 32768;
@@ -734,6 +735,15 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     __syncwarp();
     const float pscale = p.drop_post.p > 0.f ? p.drop_post.scale : 1.f;
     const uint32_t my_stage = sW + (uint32_t)(warp - 2) * 8192u;  // weight ring is free now: 8 warps x 2 x 4 KB boxes
+    if (p.tickets && p.splits > 1) {
+      // deterministic reduction order: slice s adds only after slices 0 .. s-1 of this row tile have completed theirs
+      if (lane == 0) {
+        const volatile int* tk = p.tickets + m_blk;
+        while (*tk != split) { }
+        __threadfence();
+      }
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int bx = 0; bx < ncol / 32; ++bx) {
       const int co = half * ncol + bx * 32;
@@ -764,6 +774,11 @@ fused_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.tickets && p.splits > 1) {
+      __threadfence();
+      epi_bar();                                   // all 8 warps' reductions have been performed
+      if (threadIdx.x == 64) atomicExch(p.tickets + m_blk, split + 1 == p.splits ? 0 : split + 1);
+    }
     ptx::tc_fence_before();
   }
 
@@ -1075,7 +1090,7 @@ bool fused_mlp_supported(int M, int d, int ffn, int dtype) {
   return is16(dtype) && (d == 128 || d == 256) && ffn % 128 == 0 && M > 0 && !getenv("B200ST_NO_FUSED_MLP");
 }
 int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W1, const float* b1, const void* W2, const float* b2,
-                  DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream) {
+                  DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream, int* tickets) {
   B200ST_CHECK(fused_mlp_supported(M, d, ffn, dtype), "fused MLP: unsupported shape / dtype");
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1093,7 +1108,7 @@ int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W
   MlpParams p{};
   p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
   p.b1 = b1; p.b2 = b2; p.drop_ffn = drop_ffn; p.drop_post = drop_post;
-  p.relu = 1; p.alpha = 1.f; p.mask_src = nullptr; p.mask_ld = 0;
+  p.relu = 1; p.alpha = 1.f; p.mask_src = nullptr; p.mask_ld = 0; p.tickets = tickets;
   p.idesc_g1 = ptx::make_idesc_16(128, 0, 1, dtype == BF16, dtype == BF16);
   p.idesc_g2 = ptx::make_idesc_16(d, 0, 1, dtype == BF16, dtype == BF16);
   CUtensorMap tx, tw1, tw2, tf1, tout;
@@ -1117,7 +1132,7 @@ int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W
 // Fused FFN backward, data-gradient chain: dF1 = scale * (dY W2^T) masked by (F1 > 0)  [written for the W1 weight gradient],
 // dH += dF1 W1^T (fp32, dH must be zero-initialised).  Same kernel, weights read as K-major B operands.
 int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* W1, const void* W2, const void* F1, float scale,
-                  void* dF1, float* dH, cudaStream_t stream) {
+                  void* dF1, float* dH, cudaStream_t stream, int* tickets) {
   B200ST_CHECK(fused_mlp_supported(M, d, ffn, dtype), "fused MLP: unsupported shape / dtype");
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1132,7 +1147,7 @@ int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* 
   MlpParams p{};
   p.M = M; p.d = d; p.ffn = ffn; p.splits = splits; p.chunks_per_cta = chunks / splits;
   p.b1 = nullptr; p.b2 = nullptr; p.drop_ffn = no_dropout(); p.drop_post = no_dropout();
-  p.relu = 0; p.alpha = scale; p.mask_src = F1; p.mask_ld = ffn;
+  p.relu = 0; p.alpha = scale; p.mask_src = F1; p.mask_ld = ffn; p.tickets = tickets;
   p.idesc_g1 = ptx::make_idesc_16(128, 0, 0, dtype == BF16, dtype == BF16);
   p.idesc_g2 = ptx::make_idesc_16(d, 0, 0, dtype == BF16, dtype == BF16);
   CUtensorMap tx, tw1, tw2, tf1, tout;

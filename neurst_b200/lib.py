@@ -10,7 +10,7 @@ _LIB_PATH = os.path.join(_HERE, "libb200st.so")
 _lib = None
 
 F32, BF16, F16 = 0, 1, 2
-ABI_VERSION = 200    # must equal b200st_version(): bumped whenever a struct in include/b200st.h changes layout
+ABI_VERSION = 201    # must equal b200st_version(): bumped whenever a struct in include/b200st.h changes layout
 
 
 class B200STError(RuntimeError):
@@ -161,7 +161,7 @@ class Config(C.Structure):
                 ("postprocess_dropout", C.c_float), ("label_smoothing", C.c_float),
                 ("share_src_trg_embedding", C.c_int32),
                 ("mha_self", C.c_int32), ("mha_din", C.c_int32), ("mha_dmem", C.c_int32), ("mha_dout", C.c_int32),
-                ("with_cross_attention", C.c_int32), ("disable_fused_attention", C.c_int32)]
+                ("with_cross_attention", C.c_int32), ("disable_fused_attention", C.c_int32), ("deterministic", C.c_int32)]
 
 
 class Buffers(C.Structure):

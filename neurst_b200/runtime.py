@@ -20,7 +20,7 @@ _TORCH16 = {L.BF16: torch.bfloat16, L.F16: torch.float16}
 def make_config(model_type, d, heads, ffn=0, enc_layers=0, dec_layers=0, vocab=0, src_vocab=0, feat=80, in_channels=1,
                 channels=0, conv_layer_norm=True, precision="bf16", ln_eps=1e-6, attention_dropout=0.0, ffn_dropout=0.0,
                 postprocess_dropout=0.0, label_smoothing=0.0, share_src_trg_embedding=False, mha_self=False, mha_din=0,
-                mha_dmem=0, mha_dout=0, with_cross_attention=True, disable_fused_attention=False):
+                mha_dmem=0, mha_dout=0, with_cross_attention=True, disable_fused_attention=False, deterministic=False):
     c = L.Config()
     c.model_type = model_type
     c.d, c.heads, c.ffn, c.enc_layers, c.dec_layers = d, heads, ffn, enc_layers, dec_layers
@@ -34,6 +34,7 @@ def make_config(model_type, d, heads, ffn=0, enc_layers=0, dec_layers=0, vocab=0
     c.mha_self, c.mha_din, c.mha_dmem, c.mha_dout = int(mha_self), mha_din, mha_dmem, mha_dout
     c.with_cross_attention = int(with_cross_attention)
     c.disable_fused_attention = int(disable_fused_attention)
+    c.deterministic = int(deterministic)
     return c
 
 

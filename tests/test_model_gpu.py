@@ -221,3 +221,28 @@ def test_two_graph_buckets_keep_their_own_workspace():
     rt.grads.zero_()
     float(g_big(big, 5)["loss"])
     del junk
+
+
+def test_deterministic_mode_is_reproducible():
+    """b200st_config.deterministic: the hidden slices of the fused FFN kernel reduce in slice order, so two runs of the
+    same step give bit-identical logits (and gradients equal up to the fp32 atomics of the split-K weight gradients);
+    the default mode differs run to run at the level of 16-bit roundings (fp32 sums in arrival order)."""
+    from neurst_b200 import lib as L
+    from neurst_b200.runtime import Runtime, make_config
+    cfg = dict(model="speech", d=256, heads=4, enc_layers=2, dec_layers=2, ffn=1024, channels=64, feat=80, in_channels=1, vocab=96)
+    P = R.init_params(cfg, seed=3, random_bias=True)
+    batch = U.to_cuda(U.synthetic_speech_batch(cfg, 4, 300, 16, seed=5))
+    c = make_config(L.MODEL_SPEECH, cfg["d"], cfg["heads"], cfg["ffn"], 2, 2, cfg["vocab"], channels=cfg["channels"], precision="fp16",
+                    attention_dropout=0.1, ffn_dropout=0.1, postprocess_dropout=0.1, label_smoothing=0.1, deterministic=True)
+    rt = Runtime(c)
+    rt.load_parameters(P)
+    res = []
+    for _ in range(3):
+        rt.ensure_grads().zero_()
+        b = dict(batch); b.update(training=True, seed=9, want_logits=True)
+        out = rt.run(b, backward=True)
+        torch.cuda.synchronize()
+        res.append((out["logits"].clone(), rt.grads.clone()))
+    for lg, g in res[1:]:
+        assert torch.equal(lg, res[0][0])
+        assert U.rel_err(g, res[0][1]) < 1e-6

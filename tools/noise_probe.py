@@ -8,11 +8,11 @@ from neurst_b200.runtime import Runtime, make_config
 from neurst_b200.trainer import synthetic_batch
 from oracle import restatement as R
 
-def probe(tag, prec="fp16", dropout=0.1, disable_fused=False, B=4, T=160, Lq=12):
+def probe(tag, prec="fp16", dropout=0.1, disable_fused=False, B=4, T=160, Lq=12, deterministic=False):
     cfg = dict(R.CONFIGS["speech_transformer_s"]); cfg["vocab"] = 96
     c = make_config(L.MODEL_SPEECH, cfg["d"], cfg["heads"], cfg["ffn"], cfg["enc_layers"], cfg["dec_layers"], 96, channels=256,
                     precision=prec, attention_dropout=dropout, ffn_dropout=dropout, postprocess_dropout=dropout, label_smoothing=0.1,
-                    disable_fused_attention=disable_fused)
+                    disable_fused_attention=disable_fused, deterministic=deterministic)
     rt = Runtime(c)
     rt.load_parameters(R.init_params(cfg, seed=5))
     batch = synthetic_batch(B, T, Lq, 96, seed=100, device="cuda")
@@ -28,6 +28,7 @@ def probe(tag, prec="fp16", dropout=0.1, disable_fused=False, B=4, T=160, Lq=12)
                                                                     float((lg[1] - lg[0]).abs().max())), flush=True)
 
 probe("fp16 default")
+probe("fp16 deterministic slices", deterministic=True)
 os.environ["B200ST_MLP_SPLITS"] = "1"
 probe("fp16 fused MLP, 1 hidden slice")
 del os.environ["B200ST_MLP_SPLITS"]
