@@ -344,6 +344,9 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # bounded failure with a diagnosis: if a rank is still here after the watchdog period, dump every thread's stack and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("B200ST_BENCH_WATCHDOG_S", "480")), exit=True)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
@@ -458,10 +461,18 @@ def run_gpu(args):
         if cpu is None:
             cpu = {"value": None, "unit": "frames/s", "cores": cpu_threads(), "kind": "port",
                    "sample": "oracle sample exceeded its time budget on this host (loaded CPU)"}
-    trainer.close()              # NCCL communicator of the library: closed on every rank at the same point
-    if rank != 0:
+    def leave(code=0):
+        # Multi-rank exit: every rank has passed the final barrier; the NCCL communicators (torch's and the library's) are
+        # left to the process teardown — ncclCommDestroy is an intra-node collective and a destructor-time call on one rank
+        # while another is already gone blocks forever (seen in round 2) — so the ranks exit without running destructors.
+        sys.stdout.flush(); sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            os._exit(code)
+
+    if world > 1:
+        barrier()                # rank 0 has finished its rank-0-only measurements; all ranks leave together
+    if rank != 0:
+        leave(0)
         return
 
     peaks = load_peaks()
@@ -496,18 +507,20 @@ def run_gpu(args):
     # roofline of the dominant kernel (tc_gemm_kernel: ~280 launches, ~55 % of the step): algorithmic FLOPs of those
     # launches / their durations: the GEMMs of one eagerly launched step are recorded and each is replayed back to back
     # inside the library with CUDA events around the repetitions (a graph replay cannot be bracketed per kernel).  `traffic` = DRAM bytes per launch from the committed ncu pass
-    # (profiles/r01_gemm_traffic.json, same command), averaged like `achieved`.
+    # (profiles/r02_gemm_traffic.json, same command), averaged like `achieved`.
     step_rf = {"achieved": ach, "frac": ach / peaks["tflops_sustained"], "frac_of_burst_peak": ach / peaks["tflops_burst"],
                "algorithmic_flops_per_step": fl, "mflop_per_frame": fl / (frames / world) / 1e6,
                "note": "all kernels of the step / step time"}
     traffic, ncu_share = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_total"] / max(1, tj["launches"])
-        ncu_share = tj.get("share_of_step")
-    except Exception:
-        pass
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):      # committed ncu pass of this command (latest round first)
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_total"] / max(1, tj["launches"])
+            ncu_share = tj.get("share_of_step")
+            break
+        except Exception:
+            continue
     if gemm and gemm["ms"] > 0:
         g_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05, all instantiations)", "achieved": g_tf,
@@ -529,8 +542,7 @@ def run_gpu(args):
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave(0)
 
 
 def main():
