@@ -135,7 +135,9 @@ int b200st_forward_backward(b200st_handle h, const b200st_buffers* buf, const b2
 int b200st_comm_unique_id(char* out128);
 int b200st_comm_init(b200st_handle h, const char* id128, int32_t nranks, int32_t rank);
 int b200st_comm_broadcast(b200st_handle h, float* buf, int64_t numel, int32_t root, void* stream);
-int b200st_comm_destroy(b200st_handle h);     /* call on every rank before the process group goes away */
+/* call on every rank before the process group goes away; destroy every CUDA graph that captured b200st_train_step with
+ * allreduce_grads first: ncclCommDestroy waits for the graphs that reference the communicator */
+int b200st_comm_destroy(b200st_handle h);
 int b200st_comm_stats(b200st_handle h, int64_t* reduced_elems, int32_t* calls, int32_t* world);   /* of the last step */
 struct b200st_optim_args_;
 typedef struct {

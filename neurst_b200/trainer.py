@@ -78,6 +78,12 @@ class DataParallelTrainer:
     def close(self):
         """Collective-ordered shutdown of the in-library communicator (call on every rank before leaving the job)."""
         if self.lib_comm:
+            # ncclCommDestroy waits until every CUDA graph that captured one of the communicator's collectives has been
+            # destroyed (NCCL keeps a persistent reference per capture): drop the captured steps first
+            self._graphs.clear()
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(self.rt.device)
             if self.dist:
                 self.dist.barrier()
             self.rt.comm_close()

@@ -53,6 +53,7 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         noise = float((rt.grads - local).norm() / local.norm())
         q.put((rank, err, err_g, st["reduced_elems"], st["calls"], rt.numel, noise))
+        del gs              # a live graph that captured the all-reduces keeps ncclCommDestroy waiting
         tr.close()
     finally:
         dist.barrier()
@@ -69,11 +70,16 @@ def test_bucketed_allreduce_inside_the_library_two_ranks():
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in range(2)]
+    hung = False
     for p in procs:
-        p.join(120)
+        p.join(30)
+        if p.is_alive():
+            p.terminate()
+            hung = True
     for rank, err, err_g, n_red, calls, numel, noise in res:
         print("rank %d: reduced-vs-sum rel err eager %.2e graph %.2e, run-to-run noise of the local gradients %.2e" % (rank, err, err_g, noise))
         # the reduced arena is the sum of two independently recomputed local arenas: the bound is the run-to-run noise of the
         # backward pass itself (fp32 atomics order -> 1-ulp flips of 16-bit intermediates), not of the reduction
         assert err < max(1e-5, 4 * noise) and err_g < max(1e-5, 4 * noise), (rank, err, err_g, noise)
         assert n_red == numel and calls == 4, (n_red, numel, calls)   # whole arena, in 4 buckets
+    assert not hung, "a rank did not leave after closing the communicator"
