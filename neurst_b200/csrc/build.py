@@ -98,5 +98,42 @@ def _build_locked(force, verbose):
     return OUT
 
 
+IO_OUT = os.path.join(os.path.dirname(HERE), "libb200st_io.so")
+IO_FLAGS = ["-O3", "-std=c11", "-fPIC", "-shared", "-Wall"]
+
+
+def _io_digest():
+    h = hashlib.sha256(open(os.path.join(HERE, "io_host.c"), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "..", "include", "b200st_io.h"), "rb").read())
+    h.update(" ".join(IO_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build_io(force=False):
+    """libb200st_io.so: the host-side input-edge helpers (TFRecord framing, CRC-32C) — plain C, gcc, no CUDA."""
+    import fcntl
+    os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "io_digest.txt")
+    dig = _io_digest()
+    if not force and os.path.exists(IO_OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return IO_OUT
+    with open(os.path.join(OBJ, ".lock_io"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(IO_OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+                return IO_OUT
+            tmp = IO_OUT + ".tmp.%d" % os.getpid()
+            r = subprocess.run([os.environ.get("CC", "gcc")] + IO_FLAGS + [os.path.join(HERE, "io_host.c"), "-o", tmp],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("gcc failed for io_host.c:\n%s\n%s" % (r.stdout, r.stderr))
+            os.replace(tmp, IO_OUT)
+            open(stamp, "w").write(dig)
+            return IO_OUT
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_io(force="--force" in sys.argv))

@@ -58,39 +58,56 @@ class FrameBudgetBucketer:
             self.batch_sizes = [int(batch_size_per_gpu // x) for x in b]
         else:
             self.batch_sizes = [int(minimal_multiple(batch_size_per_gpu // x, 8)) for x in b]
+        n = len(b)
         if frame_transcript_ratio is None:
-            self.trg_bounds = [self.max_trg_len] * len(b)
+            # the reference pads transcripts to the longest of each batch (padded_shapes [None]); a fixed bound keeps the
+            # shapes static for CUDA-graph capture and changes no result (padding is masked out of the loss)
+            self.trg_bounds = [self.max_trg_len] * n
+            self.trg_pairs = [[self.max_trg_len] for _ in range(n)]
         else:
             r = frame_transcript_ratio
-            tb = [int(x / (r + i * (max_src_len / self.max_trg_len - r) / len(b))) for i, x in enumerate(b)]
+            tb = [int(x / (r + i * (max_src_len / self.max_trg_len - r) / n)) for i, x in enumerate(b)]
             self.trg_bounds = [minimal_multiple(min(t, self.max_trg_len), 8) for t in tb]
+            # speech2text.py:335-343: every audio bucket accepts its own transcript bound and the next bucket's
+            self.trg_pairs = [[self.trg_bounds[i], self.trg_bounds[min(i + 1, n - 1)]] for i in range(n)]
 
-    def bucket_of(self, n_frames):
+    def bucket_of(self, n_frames, n_trg=0):
+        """example_to_bucket_id (speech2text.py:350-360): the first (audio bucket i, transcript slot j) in row-major order
+        with n_frames <= bound_i and n_trg <= trans_bound[i][j]; None when nothing matches (the reference filters such
+        examples out beforehand with clean_dataset_by_length)."""
         for i, bound in enumerate(self.boundaries):
             if n_frames <= bound:
-                return i
-        return None         # longer than max_src_len: filtered out, as the reference's dataset filter does
+                for j, tb in enumerate(self.trg_pairs[i]):
+                    if n_trg <= tb:
+                        return (i, j)
+        return None
 
     def shapes(self):
         """[(T, B per GPU, L)] — the static shape buckets (one captured CUDA graph each in the trainer)."""
-        return list(zip(self.boundaries, self.batch_sizes, self.trg_bounds))
+        out = []
+        for i, (t, bs) in enumerate(zip(self.boundaries, self.batch_sizes)):
+            for l in self.trg_pairs[i]:
+                if (t, bs, l) not in out:
+                    out.append((t, bs, l))
+        return out
 
     def batches(self, examples, pad_id=0, feature_dim=80):
         """examples: iterable of dict(audio: FloatTensor [n, F], transcript: LongTensor [l]).  Yields per-replica lists of
-        padded batches {src [B,T,F,1], src_length, trg [B,L], trg_length, trg_input}, drop_remainder like the reference."""
-        pools = [[] for _ in self.boundaries]
+        padded batches {src [B,T,F,1], src_length, trg [B,L], trg_length}; group_by_window + padded_batch(drop_remainder)
+        like the reference: a batch leaves as soon as its bucket holds batch_size x world examples."""
+        pools = {}
         for ex in examples:
-            i = self.bucket_of(ex["audio"].shape[0])
-            if i is None or ex["transcript"].numel() > self.trg_bounds[i]:
+            key = self.bucket_of(ex["audio"].shape[0], ex["transcript"].numel())
+            if key is None:
                 continue
-            pools[i].append(ex)
-            need = self.batch_sizes[i] * self.world
-            if len(pools[i]) == need:
-                group, pools[i] = pools[i], []
-                yield [self._pad(group[r::self.world], i, pad_id, feature_dim) for r in range(self.world)]
+            pool = pools.setdefault(key, [])
+            pool.append(ex)
+            if len(pool) == self.batch_sizes[key[0]] * self.world:
+                pools[key] = []
+                yield [self._pad(pool[r::self.world], key, pad_id, feature_dim) for r in range(self.world)]
 
-    def _pad(self, group, i, pad_id, feature_dim):
-        T, L, B = self.boundaries[i], self.trg_bounds[i], len(group)
+    def _pad(self, group, key, pad_id, feature_dim):
+        T, L, B = self.boundaries[key[0]], self.trg_pairs[key[0]][key[1]], len(group)
         src = torch.zeros(B, T, feature_dim, 1)
         trg = torch.full((B, L), int(pad_id), dtype=torch.long)
         sl, tl = torch.zeros(B, dtype=torch.long), torch.zeros(B, dtype=torch.long)
@@ -100,6 +117,88 @@ class FrameBudgetBucketer:
             trg[j, :l] = ex["transcript"]
             sl[j], tl[j] = n, l
         return dict(src=src, src_length=sl, trg=trg, trg_length=tl)
+
+
+class SpeechToText:
+    """Data side of the `SpeechToText` task for already extracted features and tokenised transcripts
+    (neurst/tasks/speech2text.py): get_data_preprocess_fn (:163-236), the TRAIN branch of create_and_batch_tfds (:238-384)
+    and example_to_input (:135-161).  Raw audio / raw text need the reference's extractor and text pipeline and are refused,
+    as the reference refuses raw audio ("We recommend one to preprocess the audio in advance")."""
+
+    def __init__(self, trg_meta, max_src_len, max_trg_len, batch_size_per_gpu, audio_feature_dim=80, audio_feature_channels=1,
+                 truncate_src=False, truncate_trg=False, min_src_bucket_boundary=128, frame_transcript_ratio=None,
+                 disable_batch_efficiency=False, specaug=None, world=1, padding_mode="default"):
+        if max_src_len is None:
+            raise RuntimeError("`max_src_len` for SpeechToText task must be provided.")
+        if max_trg_len is None:
+            raise RuntimeError("`max_trg_len` for SpeechToText task must be provided.")
+        self.meta = dict(trg_meta)
+        self.dim, self.channels = audio_feature_dim, audio_feature_channels
+        self.max_src_len, self.max_trg_len = max_src_len, max_trg_len
+        self.truncate_src, self.truncate_trg = truncate_src, truncate_trg
+        self.specaug = SpecAugment.build(specaug)
+        self.padding_mode = padding_mode
+        self.bucketer = FrameBudgetBucketer(batch_size_per_gpu, max_src_len, max_trg_len, min_src_bucket_boundary, world,
+                                            frame_transcript_ratio, disable_batch_efficiency)
+
+    def preprocess_fn(self, data_status, training=True, with_label=True):
+        if data_status["audio"] != "projected":
+            raise RuntimeError("We recommend one to preprocess the audio in advance.")
+        if with_label and data_status["transcript"] != "projected":
+            raise RuntimeError("raw transcripts need the reference's text pipeline (tokenizer / BPE / vocabulary): "
+                               "write the TFRecords with projected (int64) transcripts")
+        width = self.dim * self.channels
+
+        def proc(data):
+            audio = torch.as_tensor(data["audio"], dtype=torch.float32).reshape(-1)
+            if self.truncate_src and self.max_src_len:
+                audio = audio[:self.max_src_len * width]
+            ret = {"audio": audio.reshape(-1, width), "audio_length": audio.numel() // width}
+            if with_label:
+                text = torch.as_tensor(data["transcript"], dtype=torch.long).reshape(-1)
+                if training and self.truncate_trg and self.max_trg_len and text.numel() > self.max_trg_len:
+                    text = torch.cat([text[:self.max_trg_len - 1], text[-1:]])
+                ret["transcript"] = text
+            return ret
+        return proc
+
+    def keep(self, ex):
+        """clean_dataset_by_length (dataset_utils.py:326-336): drop empty samples (size <= 1) and samples beyond the maxima."""
+        a, t = ex["audio"].numel(), ex["transcript"].numel()
+        return 1 < a <= self.max_src_len * self.dim * self.channels and 1 < t <= self.max_trg_len
+
+    def train_batches(self, examples, generator=None, pin=False):
+        """examples: preprocessed samples (in the order the dataset yields them; shuffling is the caller's, as
+        `shuffle_buffer` is in the reference).  Yields, per step, the list of per-replica model inputs."""
+        pad = int(self.meta["pad_id"])
+        for per_rank in self.bucketer.batches((e for e in examples if self.keep(e)), pad_id=pad, feature_dim=self.dim * self.channels):
+            out = []
+            for b in per_rank:
+                B, T = b["src"].shape[0], b["src"].shape[1]
+                src = b["src"].reshape(B, T, self.dim, self.channels)
+                if self.specaug is not None:       # the reference augments each utterance before padding: same masks, padding untouched
+                    src = self.specaug(src, b["src_length"], generator=generator)
+                out.append(self.example_to_input(dict(audio=src, audio_length=b["src_length"], transcript=b["trg"]), pin=pin))
+            yield out
+
+    def example_to_input(self, batch, infer=False, pin=False):
+        B = batch["audio"].shape[0]
+        d = {"src": batch["audio"].reshape(B, -1, self.dim, self.channels), "src_length": batch["audio_length"].to(torch.long)}
+        bos = torch.full((B,), int(self.meta["bos_id"]), dtype=torch.long)
+        if infer:
+            d["trg_input"] = bos
+        else:
+            trg = batch["transcript"]
+            pad = int(self.meta["pad_id"])
+            if self.padding_mode == "default":                     # deduce_text_length (models/model_utils.py:23-41)
+                d["trg_length"] = (trg != pad).sum(1)
+            else:                                                  # EOS_AS_PADDING: first pad (= eos) position + 1
+                d["trg_length"] = (trg != pad).to(torch.int32).argmin(-1) + 1
+            d["trg"] = trg
+            d["trg_input"] = torch.cat([bos[:, None], trg[:, :-1]], 1)
+        if pin and torch.cuda.is_available():
+            d = {k: v.contiguous().pin_memory() for k, v in d.items()}
+        return d
 
 
 class SpecAugment:

@@ -22,6 +22,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.b200st_version() == L.ABI_VERSION
 
 
+def test_io_library_exports_every_declared_symbol():
+    import ctypes
+    from neurst_b200.csrc import build as B
+    header = open(os.path.join(ROOT, "include", "b200st_io.h")).read()
+    declared = set(re.findall(r"\b(b200st_[a-z0-9_]+)\s*\(", header))
+    assert declared == {"b200st_io_version", "b200st_crc32c", "b200st_crc32c_mask", "b200st_tfrecord_index", "b200st_tfrecord_frame"}
+    lib = ctypes.CDLL(B.build_io())
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
 def test_parameter_table_matches_reference_layouts():
     lib = L.load()
     for name in ("speech_transformer_toy", "speech_transformer_s", "speech_transformer_m"):
