@@ -1,5 +1,6 @@
 // Shared device/host helpers for libb200st (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -95,21 +96,24 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- counter-based RNG for dropout: Philox4x32-10 --------------------------------------
+// ---- counter-based RNG for dropout: Philox4x32-7 ---------------------------------------
+// (7 rounds: the smallest round count of Philox4x32 that Salmon et al. report as passing BigCrush; the generator of all
+// keep-bits of a step is integer-ALU bound — 0.26 ms of the cfg-2 step with 10 rounds, measured by tools/ablate_step.py)
 // One call yields 4 x 32 random bits for counter (idx4, stream) under key (seed).  Dropout at element
 // index e uses call (e >> 2) and lane (e & 3), so forward and backward regenerate identical masks.
 struct Philox4 { uint32_t x, y, z, w; };
+constexpr int kPhiloxRounds = 7;
 __host__ __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
   uint64_t p = (uint64_t)a * (uint64_t)b;
   *hi = (uint32_t)(p >> 32);
   return (uint32_t)p;
 }
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t counter, uint64_t stream) {
+__host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t counter, uint64_t stream) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32);
   uint32_t c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     uint32_t hi0, hi1;
     uint32_t lo0 = mulhilo32(0xD2511F53u, c0, &hi0);
     uint32_t lo1 = mulhilo32(0xCD9E8D57u, c2, &hi1);
@@ -126,7 +130,7 @@ __host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
   return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
 }
 __host__ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t stream, uint64_t group, uint32_t thresh) {
-  const Philox4 r = philox4x32_10(seed, group, stream);
+  const Philox4 r = philox4x32(seed, group, stream);
   uint32_t m = 0;
   m |= ((r.x & 0xffffu) >= thresh ? 1u : 0u) << 0; m |= ((r.x >> 16) >= thresh ? 1u : 0u) << 1;
   m |= ((r.y & 0xffffu) >= thresh ? 1u : 0u) << 2; m |= ((r.y >> 16) >= thresh ? 1u : 0u) << 3;
@@ -157,5 +161,14 @@ __device__ __forceinline__ bool drop_keep1(const DropoutSpec& d, uint64_t e) {
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Measurement aid (tools/ablate_step.py): B200ST_ABLATE is a bit mask of kernel classes whose launches are SKIPPED, to
+// read each class's contribution to the step off the critical path (results are garbage while it is set).
+enum : int { ABL_COLSUM = 1, ABL_WGRAD = 2, ABL_LN_FWD = 4, ABL_LN_BWD = 8, ABL_ATTN_FWD = 16, ABL_ATTN_BWD = 32, ABL_MLP_FWD = 64,
+              ABL_MLP_BWD = 128, ABL_GEMM = 256, ABL_OPTIM = 512, ABL_DROPBITS = 1024, ABL_CONV = 2048 };
+inline int ablate_mask() {
+  const char* e = getenv("B200ST_ABLATE");
+  return e ? atoi(e) : 0;
+}
 
 }  // namespace b200st

@@ -70,6 +70,8 @@ __device__ __forceinline__ float gemm_epilogue_value(const GemmEpilogue& ep, flo
 // Host launchers (return 0 on success; message via set_last_error).
 int gemm_simt_f32(const GemmArgs& g, cudaStream_t stream);
 int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream);
+// weight gradients of one backward block in one launch; returns 2 when the group does not qualify (nothing launched), 1 on error
+int gemm_wgrad_group(const GemmArgs* gs, int n, cudaStream_t stream);
 // Dispatch on operand dtype: F32 operands -> SIMT fp32 FMA kernel, BF16 operands -> tcgen05 kernel.
 int gemm(const GemmArgs& g, cudaStream_t stream);
 

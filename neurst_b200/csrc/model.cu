@@ -242,6 +242,10 @@ struct Ctx {
     }
     return (M + 127) / 128 <= 4096 ? tickets : nullptr;
   }
+  // weight gradients of the current backward block, launched together by flush_wgrads()
+  struct PendingWgrad { GemmArgs g; float* db; const void* dY; int M, N; int64_t ldy; };
+  std::vector<PendingWgrad> pending_wgrads;
+  bool defer_wgrads = false;
   bool dry;        // planning pass: allocate only, launch nothing
   bool training;
   uint64_t seed;
@@ -359,12 +363,47 @@ static int linear_wgrad(Ctx& c, const void* X, int64_t ldx, const void* dY, int6
   g.C = c.G(w); g.c_dtype = F32; g.ldc = N;
   g.epi.accumulate = 1;
   g.splitk = 0;
+  if (c.defer_wgrads) {      // inside a backward block: launched together at the end of the block (flush_wgrads)
+    c.pending_wgrads.push_back(Ctx::PendingWgrad{g, b.empty() ? nullptr : c.G(b), dY, M, N, ldy});
+    return 0;
+  }
   cudaStream_t ws = c.wgrad_stream();
   RUN(gemm(g, ws));
   if (!b.empty()) RUN(colsum_accum(dY, c.adt, M, N, ldy, c.G(b), ws));
   c.wgrad_done(ws);
   return 0;
 }
+// End of a backward block: the block's weight gradients as ONE grouped launch (tc_gemm.cu: tc_wgrad_group_kernel) when they
+// qualify, one by one otherwise; the bias gradients behind it.  All their inputs (the block's dY buffers in the current
+// scratch parity, saved activations) were produced on `st` before this point and stay untouched until block i+2.
+static int flush_wgrads(Ctx& c) {
+  if (c.pending_wgrads.empty()) return 0;
+  std::vector<Ctx::PendingWgrad> pend;
+  pend.swap(c.pending_wgrads);
+  cudaStream_t ws = c.wgrad_stream();
+  if (!c.dry) {
+    GemmArgs gs[4];
+    const int n = (int)pend.size();
+    int grouped = 2;           // 2 = not grouped: one launch per product
+    if (n >= 2 && n <= 4 && is16(c.adt)) {
+      for (int i = 0; i < n; ++i) gs[i] = pend[i].g;
+      grouped = gemm_wgrad_group(gs, n, ws);
+      if (grouped != 0 && grouped != 2) return grouped;
+    }
+    if (grouped != 0)
+      for (const auto& w : pend) B200ST_TRY(gemm(w.g, ws));
+    for (const auto& w : pend)
+      if (w.db) B200ST_TRY(colsum_accum(w.dY, c.adt, w.M, w.N, w.ldy, w.db, ws));
+  }
+  c.wgrad_done(ws);
+  return 0;
+}
+struct WgradBlock {          // scope of one backward block: defers linear_wgrad launches until flush()
+  Ctx& c;
+  explicit WgradBlock(Ctx& cc) : c(cc) { c.defer_wgrads = true; }
+  int flush() { c.defer_wgrads = false; return flush_wgrads(c); }
+  ~WgradBlock() { c.defer_wgrads = false; }
+};
 
 // ---- attention core on projected q/k/v views ----------------------------------------------------
 struct View { void* ptr; int64_t ld; };   // [B*T, ld] row-major, heads at column offset h*dh
@@ -537,6 +576,7 @@ static int self_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_in
 
 static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, float* dx_in, Scratch& sc, const AttnSave& sv) {
   sc.select(c.begin_bwd_block());
+  WgradBlock wb(c);
   const Config& cf = c.m.cfg;
   const int d = cf.d, M = sv.dims.B * sv.dims.Tq;
   if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
@@ -551,7 +591,7 @@ static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_o
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, 3 * d, M, d, 3 * d, pre + ".qkv.kernel", pre + ".qkv.bias"));
   B200ST_TRY(linear_dgrad(c, sc.dqkv, 3 * d, M, 3 * d, d, pre + ".qkv.kernel", e0, sc.dh, F32, d));
   B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
-  return 0;
+  return wb.flush();
 }
 
 // cross attention: q from LN(x), k/v from memory (act dtype, [B*Tm, d]); memory_bias [B,Tm]
@@ -591,6 +631,7 @@ static int cross_attn_block_fwd(Ctx& c, const std::string& pre, const float* x_i
 static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, float* dx_in, float* dmem, Scratch& sc,
                                 const AttnSave& sv) {
   sc.select(c.begin_bwd_block());
+  WgradBlock wb(c);
   const Config& cf = c.m.cfg;
   const int d = cf.d, M = sv.dims.B * sv.dims.Tq, Mk = sv.dims.B * sv.dims.Tk;
   if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
@@ -609,7 +650,7 @@ static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_
   GemmEpilogue ea = gemm_defaults().epi;
   ea.accumulate = 1;                              // memory gradient accumulates over decoder layers
   B200ST_TRY(linear_dgrad(c, sc.dkv, 2 * d, Mk, 2 * d, d, pre + ".kv.kernel", ea, dmem, F32, d));
-  return 0;
+  return wb.flush();
 }
 
 // x_out = x_in + dropout(W2 dropout(relu(W1 LN(x_in)))) (common_layers.py:145-160)
@@ -648,6 +689,7 @@ static int ffn_block_fwd(Ctx& c, const std::string& pre, const float* x_in, floa
 
 static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, float* dx_in, Scratch& sc, const FfnSave& sv) {
   sc.select(c.begin_bwd_block());
+  WgradBlock wb(c);
   const Config& cf = c.m.cfg;
   const int d = cf.d, f = cf.ffn, M = sv.M;
   if (c.dy_ready) c.dy_ready = false;      // produced by the previous block's LayerNorm-backward
@@ -662,7 +704,7 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
                       fd.p > 0.f ? fd.scale : 1.f, sc.dF1, sc.dh, c.st, tk));
     B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dF1, f, M, d, f, pre + ".w1", pre + ".b1"));
     B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
-    return 0;
+    return wb.flush();
   }
   GemmEpilogue e1 = gemm_defaults().epi;
   e1.mask_src = sv.f1; e1.mask_dtype = c.adt; e1.mask_ld = f;      // relu' and ffn-dropout mask: stored f1 > 0
@@ -673,7 +715,7 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
   GemmEpilogue e0 = gemm_defaults().epi;
   B200ST_TRY(linear_dgrad(c, sc.dF1, f, M, f, d, pre + ".w1", e0, sc.dh, F32, d));
   B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
-  return 0;
+  return wb.flush();
 }
 
 // ---- stacks ----------------------------------------------------------------------------------------

@@ -414,6 +414,186 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 
 // =============================================================================================================
+// Grouped weight-gradient GEMM: up to kMaxGroup products  dW_g[K_in, N_out] += X_g^T dY_g  of one backward block in ONE
+// persistent launch (TF autodiff of the Dense / einsum sites of a sublayer: neurst/layers/common_layers.py:270-288,
+// multi_head_attention.py:145-215).  Each product alone has 2..16 output tiles and needs split-K over the B*T rows to fill
+// 148 SMs, i.e. every CTA reduce-adds a full 128 x 256 fp32 tile for a handful of k-blocks of MMA work and every launch pays
+// the fixed ~6 us; together the products of a block give one wave of work units with k-ranges 3-4x longer (tools/ablate_step.py:
+// the weight-gradient launches cost 0.84 ms of the 6.46 ms cfg-2 step although they run on the side stream).
+// Same pipeline as tc_gemm_kernel<256, true, true, OUT_ATOMIC>; a work unit = (product, m tile, n tile, k split).
+// =============================================================================================================
+constexpr int kMaxGroup = 4;
+struct TcGroupProb {
+  CUtensorMap ta, tb, tc;
+  int m_tiles, n_tiles, splitk, kb_total, kb_per_split, tile_begin;
+  float alpha;
+  int pad_;
+};
+struct TcGroup {
+  TcGroupProb prob[kMaxGroup];
+  int n, num_tiles, stages;
+  uint32_t idesc;
+};
+struct GroupTile { int gi, m_blk, n_blk, kb0, kb1; };
+__device__ __forceinline__ GroupTile group_tile(const TcGroup& g, int tile) {
+  GroupTile t;
+  t.gi = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroup; ++i)
+    if (i < g.n && tile >= g.prob[i].tile_begin) t.gi = i;
+  const TcGroupProb& q = g.prob[t.gi];
+  int local = tile - q.tile_begin;
+  const int split = local % q.splitk; local /= q.splitk;
+  t.n_blk = local % q.n_tiles;
+  t.m_blk = local / q.n_tiles;
+  t.kb0 = split * q.kb_per_split;
+  t.kb1 = min(q.kb_total, t.kb0 + q.kb_per_split);
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_wgrad_group_kernel(const __grid_constant__ TcGroup grp) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int BN = 256;
+  constexpr uint32_t kBBytes = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kMnLbo = 64u * BK * 2, kMnSbo = 1024u, kMnKstep = 16u * 128u;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = grp.stages;
+  const uint32_t stage_out = smem_base + stages * kStageBytes;
+  const uint32_t bar_base = stage_out + kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < grp.n; ++i) {
+      ptx::prefetch_tensormap(&grp.prob[i].ta);
+      ptx::prefetch_tensormap(&grp.prob[i].tb);
+      ptx::prefetch_tensormap(&grp.prob[i].tc);
+    }
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 8); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < grp.num_tiles; tile += gridDim.x) {
+        const GroupTile t = group_tile(grp, tile);
+        const CUtensorMap* ma = &grp.prob[t.gi].ta;
+        const CUtensorMap* mb = &grp.prob[t.gi].tb;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          ptx::mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c)
+            ptx::tma_load_4d(sa + c * (64 * BK * 2), ma, full_bar(stage), t.m_blk * BM + c * 64, kb * BK, 0, 0);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            ptx::tma_load_4d(sb + c * (64 * BK * 2), mb, full_bar(stage), t.n_blk * BN + c * 64, kb * BK, 0, 0);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < grp.num_tiles; tile += gridDim.x) {
+        const GroupTile t = group_tile(grp, tile);
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = ptx::make_smem_desc_sw128(sa + k * kMnKstep, kMnLbo, kMnSbo);
+            const uint64_t db = ptx::make_smem_desc_sw128(sb + k * kMnKstep, kMnLbo, kMnSbo);
+            ptx::mma_f16_ss(tmem_d, da, db, grp.idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(empty_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t my_stage = stage_out + (uint32_t)(warp - 2) * 8192u;
+    for (int tile = blockIdx.x; tile < grp.num_tiles; tile += gridDim.x) {
+      const GroupTile t = group_tile(grp, tile);
+      const CUtensorMap* mc = &grp.prob[t.gi].tc;
+      const float alpha = grp.prob[t.gi].alpha;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const int c_begin = half * (BN / 2);
+#pragma unroll 1
+      for (int bx = 0; bx < BN / 2 / 32; ++bx) {
+        const uint32_t buf = my_stage + (uint32_t)(bx & 1) * 4096u;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const int co = c_begin + bx * 32;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr_row + (uint32_t)co, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
+        stage_chunk<OUT_ATOMIC>(buf, lane, 0, v);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int cn = t.n_blk * BN + co, cm = t.m_blk * BM + quad * 32;
+          asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(mc), "r"(buf), "r"(cn), "r"(cm), "r"(0), "r"(0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// =============================================================================================================
 // Fused Transformer FFN forward:  x_out += dropout_post( dropout_ffn(relu(X W1 + b1)) W2 + b2 )
 //   neurst/layers/common_layers.py:145-160 (TransformerFFN) inside the pre-norm wrapper (:73-85); X = LN(x_in) (16-bit),
 //   x_out is pre-initialised with the residual x_in by the LayerNorm kernel.
@@ -906,7 +1086,7 @@ namespace {
 // end is RECORDED (arguments only); tc_profile_end() then replays each recorded GEMM back to back (1 warm-up + kReps timed
 // launches bracketed by one event pair, no host gap between them) and reports the per-launch average.  The buffers of the
 // step are still alive (same workspace), accumulate / reduce epilogues only add into gradients nobody reads afterwards.
-struct ProfRec { GemmArgs g; cudaStream_t stream; int bn, splitk; };
+struct ProfRec { GemmArgs g; cudaStream_t stream; int bn, splitk; int group_n = 0; GemmArgs rest[3]; };   // group_n > 1: grouped weight-gradient launch (g + rest)
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
 
@@ -956,6 +1136,10 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   // the instruction descriptor encodes them separately — so the library refuses mixed products up front
   B200ST_CHECK(g.A.dtype == g.B.dtype, "tcgen05 kind::f16 needs A and B in the same 16-bit format (both bf16 or both fp16)");
   B200ST_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "empty GEMM");
+  if (const int abl = ablate_mask()) {
+    const bool wgrad = g.A.mn_major && g.B.mn_major;
+    if ((wgrad && (abl & ABL_WGRAD)) || (!wgrad && (abl & ABL_GEMM))) return 0;
+  }
   if (g_num_sms == 0) {
     int dev = 0;
     B200ST_CUDA(cudaGetDevice(&dev));
@@ -1084,6 +1268,86 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
 }
 
 
+// One launch for the weight gradients of a backward block (see tc_wgrad_group_kernel).  Every product must be a plain
+// fp32-accumulate MN-major x MN-major 16-bit GEMM with M % 128 == 0 and N % 256 == 0; returns 2 (nothing launched) when the
+// group does not qualify, so that the caller issues the products one by one.
+int gemm_wgrad_group(const GemmArgs* gs, int n, cudaStream_t stream) {
+  if (n < 2 || n > kMaxGroup || getenv("B200ST_NO_GROUPED_WGRAD")) return 2;
+  for (int i = 0; i < n; ++i) {
+    const GemmArgs& g = gs[i];
+    const bool plain = !g.epi.relu && !g.epi.mask_src && g.epi.drop.p == 0.f && !g.epi.residual && !g.epi.bias && g.epi.accumulate;
+    if (!(is16(g.A.dtype) && g.A.dtype == g.B.dtype && g.A.dtype == gs[0].A.dtype && g.A.mn_major && g.B.mn_major && plain &&
+          g.c_dtype == F32 && g.nb1 == 1 && g.nb2 == 1 && g.M % BM == 0 && g.N % 256 == 0 && g.K > 0 && g.splitk <= 1 &&
+          (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc * 4) % 16 == 0))
+      return 2;
+  }
+  if (ablate_mask() & ABL_WGRAD) return 0;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B200ST_CUDA(cudaGetDevice(&dev));
+    B200ST_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const TcDebug& dbg = tc_debug();
+  const int num_sms = dbg.max_ctas > 0 ? dbg.max_ctas : (dbg.reserve_sms > 0 && dbg.reserve_sms < g_num_sms ? g_num_sms - dbg.reserve_sms : g_num_sms);
+  TcGroup grp;
+  std::memset(&grp, 0, sizeof(grp));
+  grp.n = n;
+  int64_t work = 0;
+  int tiles0[kMaxGroup], kbt[kMaxGroup];
+  for (int i = 0; i < n; ++i) {
+    tiles0[i] = (gs[i].M / BM) * (gs[i].N / 256);
+    kbt[i] = ceil_div(gs[i].K, BK);
+    work += (int64_t)tiles0[i] * kbt[i];
+  }
+  // smallest common k-range L (in 64-row blocks) whose work units fit one wave of `num_sms` CTAs
+  int L = (int)((work + num_sms - 1) / num_sms);
+  if (L < 2) L = 2;
+  for (;; ++L) {
+    int64_t units = 0;
+    for (int i = 0; i < n; ++i) units += (int64_t)tiles0[i] * ceil_div(kbt[i], L);
+    if (units <= num_sms || L >= 4096) break;
+  }
+  int tile = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmArgs& g = gs[i];
+    TcGroupProb& q = grp.prob[i];
+    q.m_tiles = g.M / BM; q.n_tiles = g.N / 256; q.kb_total = kbt[i];
+    q.kb_per_split = L < kbt[i] ? L : kbt[i];
+    q.splitk = ceil_div(kbt[i], q.kb_per_split);
+    q.tile_begin = tile;
+    q.alpha = g.epi.alpha;
+    tile += q.m_tiles * q.n_tiles * q.splitk;
+    B200ST_TRY(make_operand_map(g.A, g.M, g.K, 1, 1, BM, &q.ta));
+    B200ST_TRY(make_operand_map(g.B, g.N, g.K, 1, 1, 256, &q.tb));
+    B200ST_TRY(make_out_map(g.C, F32, g.N, g.M, 1, 1, g.ldc, 0, 0, &q.tc));
+  }
+  grp.num_tiles = tile;
+  const uint32_t stage_bytes = kABytes + 256u * BK * 2;
+  int stages = (int)((kSmemLimit - (int)kStagingBytes - 2048) / stage_bytes);
+  if (stages > 8) stages = 8;
+  grp.stages = stages;
+  grp.idesc = ptx::make_idesc_16(256, 1, 1, gs[0].A.dtype == BF16, gs[0].B.dtype == BF16);
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 8 * (2 * stages + 5) + 16;
+  B200ST_CHECK(smem <= (size_t)kSmemLimit, "smem budget exceeded");
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200ST_CUDA(cudaFuncSetAttribute(tc_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  const int grid = grp.num_tiles < num_sms ? grp.num_tiles : num_sms;
+  ++g_launches;
+  if (g_prof) {
+    ProfRec r{gs[0], stream, 256, grp.prob[0].splitk};
+    r.group_n = n;
+    for (int i = 1; i < n; ++i) r.rest[i - 1] = gs[i];
+    g_prof_recs.push_back(r);
+  }
+  launch_pdl(tc_wgrad_group_kernel, grid, kThreads, smem, stream, grp);
+  B200ST_LAUNCH_CHECK();
+  return 0;
+}
+
+
 // Fused FFN forward (see fused_mlp_fwd_kernel).  X: 16-bit [M, d] (LayerNorm output); W1 [d, ffn], W2 [ffn, d] in the same
 // 16-bit type (TF layouts); F1 out [M, ffn] (saved for the backward pass); x_out fp32 [M, d] must already hold the residual.
 bool fused_mlp_supported(int M, int d, int ffn, int dtype) {
@@ -1091,6 +1355,7 @@ bool fused_mlp_supported(int M, int d, int ffn, int dtype) {
 }
 int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W1, const float* b1, const void* W2, const float* b2,
                   DropoutSpec drop_ffn, DropoutSpec drop_post, void* F1, float* x_out, cudaStream_t stream, int* tickets) {
+  if (ablate_mask() & ABL_MLP_FWD) return 0;
   B200ST_CHECK(fused_mlp_supported(M, d, ffn, dtype), "fused MLP: unsupported shape / dtype");
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1133,6 +1398,7 @@ int fused_mlp_fwd(const void* X, int dtype, int M, int d, int ffn, const void* W
 // dH += dF1 W1^T (fp32, dH must be zero-initialised).  Same kernel, weights read as K-major B operands.
 int fused_mlp_bwd(const void* dY, int dtype, int M, int d, int ffn, const void* W1, const void* W2, const void* F1, float scale,
                   void* dF1, float* dH, cudaStream_t stream, int* tickets) {
+  if (ablate_mask() & ABL_MLP_BWD) return 0;
   B200ST_CHECK(fused_mlp_supported(M, d, ffn, dtype), "fused MLP: unsupported shape / dtype");
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1186,19 +1452,24 @@ int tc_profile_end(double* ms, double* flops, int64_t* launches) {
   recs.swap(g_prof_recs);
   for (const ProfRec& r : recs) {
     const cudaStream_t st = r.stream;
-    B200ST_TRY(gemm_tc_bf16(r.g, st));                          // warm-up (tensor maps, instruction cache)
+    GemmArgs grp_args[4];
+    grp_args[0] = r.g;
+    for (int i = 1; i < r.group_n; ++i) grp_args[i] = r.rest[i - 1];
+    auto run = [&]() -> int { return r.group_n > 1 ? gemm_wgrad_group(grp_args, r.group_n, st) : gemm_tc_bf16(r.g, st); };
+    B200ST_TRY(run());                                          // warm-up (tensor maps, instruction cache)
     B200ST_CUDA(cudaEventRecord(e0, st));
-    for (int i = 0; i < kReps; ++i) B200ST_TRY(gemm_tc_bf16(r.g, st));
+    for (int i = 0; i < kReps; ++i) B200ST_TRY(run());
     B200ST_CUDA(cudaEventRecord(e1, st));
     B200ST_CUDA(cudaEventSynchronize(e1));
     float t = 0.f;
     B200ST_CUDA(cudaEventElapsedTime(&t, e0, e1));
     t /= kReps;
-    const double fl = 2.0 * (double)r.g.M * r.g.N * r.g.K * (double)r.g.nb1 * r.g.nb2;
+    double fl = 2.0 * (double)r.g.M * r.g.N * r.g.K * (double)r.g.nb1 * r.g.nb2;
+    for (int i = 1; i < r.group_n; ++i) fl += 2.0 * (double)grp_args[i].M * grp_args[i].N * grp_args[i].K;
     const int epi = (r.g.epi.bias ? 1 : 0) | (r.g.epi.relu ? 2 : 0) | (r.g.epi.mask_src ? 4 : 0) | (r.g.epi.drop.p > 0.f ? 8 : 0) |
                     (r.g.epi.residual ? 16 : 0) | (r.g.c_dtype == F32 ? 32 : 0);
-    if (dump) fprintf(dump, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", r.g.M, r.g.N, r.g.K, r.g.nb1 * r.g.nb2, r.bn, r.splitk,
-                      r.g.A.mn_major, r.g.B.mn_major, epi, t * 1e3, fl / (t * 1e-3) / 1e12);
+    if (dump) fprintf(dump, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", r.g.M, r.g.N, r.g.K, r.group_n > 1 ? -r.group_n : r.g.nb1 * r.g.nb2, r.bn,
+                      r.splitk, r.g.A.mn_major, r.g.B.mn_major, epi, t * 1e3, fl / (t * 1e-3) / 1e12);   // batch = -n: grouped launch of n products (first one listed)
     tms += t; tf += fl;
   }
   if (dump) fclose(dump);
