@@ -423,12 +423,14 @@ __global__ void __launch_bounds__(256, (CPL <= 8 ? 2 : 1)) conv1_bwd_fused_kerne
 // Backward from the saved normalised activations (C == 256, Cin == 1): col2im gather of dcol + ReLU' + LN' with xhat and
 // 1/sigma read back (no convolution recompute, no statistics), db/dgamma/dbeta partials, fbank im2col rows for dW1.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+// IMPLICIT: `dcol` is the class-major tiled input gradient written by the implicit conv2 data-gradient GEMMs
+// (tc_gemm.cu: conv2_dgrad_implicit) — one row per position instead of up to four tap rows to gather.
+template <typename T, bool IMPLICIT>
 __global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
     const float* __restrict__ src, const T* __restrict__ gamma, const T* __restrict__ beta, const T* __restrict__ xhat,
     const float* __restrict__ rstd, const T* __restrict__ dcol, T* __restrict__ dz1, T* __restrict__ col1, int K1p,
     float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int Tn, int F, int T1, int F1, int T2,
-    int F2) {
+    int F2, int tu, int ub) {
   pdl_wait();
   pdl_trigger();
   constexpr int C = 256;
@@ -462,6 +464,12 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
       }
       L.xh.load(xhat + p * C + 8 * lane);
       L.rs = __ldg(rstd + p);
+      if (IMPLICIT) {
+        const int cls = ((tt1 & 1) << 1) | (ff1 & 1), u = tt1 >> 1, v = ff1 >> 1;
+        const int64_t row = (((int64_t)cls * B + bb) * ub + u / tu) * 128 + (u % tu) * F2 + v;
+        L.dc[0].load(dcol + row * C + 8 * lane);
+        return;
+      }
       // col2im: t1 even -> kh = 1 ; t1 odd -> kh in {0, 2} (same along f); slot = 2 * a + c2
       const int kh0 = (tt1 & 1) ? 0 : 1, kw0 = (ff1 & 1) ? 0 : 1;
 #pragma unroll
@@ -484,11 +492,13 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
       float xh[8], d[8], t8[8];
       cur.xh.get(xh);
       cur.dc[0].get(d);
+      if (!IMPLICIT) {
 #pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        cur.dc[k].get(t8);
+        for (int k = 1; k < 4; ++k) {
+          cur.dc[k].get(t8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] += t8[i];
+          for (int i = 0; i < 8; ++i) d[i] += t8[i];
+        }
       }
       const float rs = cur.rs;
       float c1 = 0.f, c2s = 0.f;
@@ -745,7 +755,7 @@ int conv1_bwd_fused(const float* src, const float* w, const float* b, const floa
 // backward of the normalised-save front-end (C == 256, Cin == 1, 16-byte aligned rows)
 int conv1_bwd_from_xhat(const float* src, const void* gamma, const void* beta, const void* xhat, const float* rstd,
                         const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma, float* dbeta, int B,
-                        int T, int F, int C, cudaStream_t s) {
+                        int T, int F, int C, cudaStream_t s, int implicit_tiles) {
   if (ablate_mask() & ABL_CONV) return 0;
   B200ST_CHECK(C == 256 && K1p >= 9 && K1p <= 32, "conv1_bwd_from_xhat supports C == 256, Cin == 1");
   B200ST_CHECK(((reinterpret_cast<uintptr_t>(xhat) | reinterpret_cast<uintptr_t>(dcol) | reinterpret_cast<uintptr_t>(dz1) |
@@ -754,8 +764,15 @@ int conv1_bwd_from_xhat(const float* src, const void* gamma, const void* beta, c
   const int64_t npos = (int64_t)B * T1 * F1;
   if (npos == 0) return 0;
   const int grid = pick_grid(npos, 8 * 16, 148 * 2);
-  DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT>, grid, 256, 0, s, src, (const TT*)gamma, (const TT*)beta, (const TT*)xhat, rstd,
-                                        (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2)));
+  const int tu = F2 > 0 && F2 <= 128 ? 128 / F2 : 1, ub = (T2 + tu - 1) / tu;
+  if (implicit_tiles) {
+    B200ST_CHECK(F2 <= 128, "implicit conv2 dgrad layout needs F2 <= 128");
+    DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT, true>, grid, 256, 0, s, src, (const TT*)gamma, (const TT*)beta, (const TT*)xhat, rstd,
+                                          (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2, tu, ub)));
+  } else {
+    DISPATCH_DTYPE(dtype, TT, (launch_pdl(conv1_bwd_xhat_c256_kernel<TT, false>, grid, 256, 0, s, src, (const TT*)gamma, (const TT*)beta, (const TT*)xhat, rstd,
+                                          (const TT*)dcol, (TT*)dz1, (TT*)col1, K1p, db, dgamma, dbeta, B, T, F, T1, F1, T2, F2, tu, ub)));
+  }
   ++g_kernel_launches;
   B200ST_LAUNCH_CHECK();
   return 0;

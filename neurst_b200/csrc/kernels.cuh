@@ -135,6 +135,9 @@ int im2col_3x3s2_affine(const void* y1, void* col, int dtype, int B, int T1, int
                         cudaStream_t s);   // gamma / beta in the activation dtype (bf16 shadow or fp32 master)
 int conv1_bwd_from_xhat(const float* src, const void* gamma, const void* beta, const void* xhat, const float* rstd,
                         const void* dcol, int dtype, void* dz1, void* col1, int K1p, float* db, float* dgamma, float* dbeta, int B,
-                        int T, int F, int C, cudaStream_t s);
+                        int T, int F, int C, cudaStream_t s, int implicit_tiles = 0);
+// conv2 data gradient as four implicit GEMMs (tc_gemm.cu); da = class-major padded tiles, conv2_dgrad_implicit_elems() elements
+int conv2_dgrad_implicit(const void* dy, const void* w16, void* da, int dtype, int B, int T2, int F2, int C, cudaStream_t stream);
+int64_t conv2_dgrad_implicit_elems(int B, int T2, int F2, int C);
 
 }  // namespace b200st

@@ -149,7 +149,13 @@ static SideStream& side_stream() {
   if (!init) {
     init = true;
     if (!getenv("B200ST_NO_SIDE_STREAM")) {
-      ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+      // weight gradients are filler work: with B200ST_SIDE_PRIORITY the side stream gets the lowest priority, so CTAs of the
+      // backward chain win whenever both have blocks waiting for an SM
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      const bool low = getenv("B200ST_SIDE_PRIORITY") != nullptr;
+      ss.ok = (low ? cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, lo)
+                   : cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking)) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.done[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ss.done[1], cudaEventDisableTiming) == cudaSuccess &&
@@ -398,6 +404,7 @@ static int flush_wgrads(Ctx& c) {
   c.wgrad_done(ws);
   return 0;
 }
+static bool late_flush() { static const bool v = getenv("B200ST_LATE_FLUSH") != nullptr; return v; }
 struct WgradBlock {          // scope of one backward block: defers linear_wgrad launches until flush()
   Ctx& c;
   explicit WgradBlock(Ctx& cc) : c(cc) { c.defer_wgrads = true; }
@@ -589,6 +596,7 @@ static int self_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_o
   B200ST_TRY(attention_bwd(c, sv.dims, q, k, v, sv.p_pre, sv.p_drop, c.drop(cf.attention_dropout, sv.s_attn), sc.dctx, sc.S, sc.dS,
                            dq, dk, dv, sv.ctx, sv.lse, sv.bias, sv.causal, sc.dq32));
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, 3 * d, M, d, 3 * d, pre + ".qkv.kernel", pre + ".qkv.bias"));
+  if (!late_flush()) B200ST_TRY(wb.flush());      // every dY of the block exists: the side stream starts under the rest of the chain
   B200ST_TRY(linear_dgrad(c, sc.dqkv, 3 * d, M, 3 * d, d, pre + ".qkv.kernel", e0, sc.dh, F32, d));
   B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
   return wb.flush();
@@ -644,9 +652,10 @@ static int cross_attn_block_bwd(Ctx& c, const std::string& pre, const float* dx_
   B200ST_TRY(attention_bwd(c, sv.dims, q, k, v, sv.p_pre, sv.p_drop, c.drop(cf.attention_dropout, sv.s_attn), sc.dctx, sc.S, sc.dS,
                            dq, dk, dv, sv.ctx, sv.lse, sv.bias, 0, sc.dq32));
   B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dqkv, d, M, d, d, pre + ".q.kernel", pre + ".q.bias"));
+  B200ST_TRY(linear_wgrad(c, sv.mem, d, sc.dkv, 2 * d, Mk, d, 2 * d, pre + ".kv.kernel", pre + ".kv.bias"));
+  if (!late_flush()) B200ST_TRY(wb.flush());
   B200ST_TRY(linear_dgrad(c, sc.dqkv, d, M, d, d, pre + ".q.kernel", e0, sc.dh, F32, d));
   B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
-  B200ST_TRY(linear_wgrad(c, sv.mem, d, sc.dkv, 2 * d, Mk, d, 2 * d, pre + ".kv.kernel", pre + ".kv.bias"));
   GemmEpilogue ea = gemm_defaults().epi;
   ea.accumulate = 1;                              // memory gradient accumulates over decoder layers
   B200ST_TRY(linear_dgrad(c, sc.dkv, 2 * d, Mk, 2 * d, d, pre + ".kv.kernel", ea, dmem, F32, d));
@@ -703,6 +712,7 @@ static int ffn_block_bwd(Ctx& c, const std::string& pre, const float* dx_out, fl
     RUN(fused_mlp_bwd(sc.dY, c.adt, M, d, f, c.W(pre + ".w1", 0, f).ptr, c.W(pre + ".w2", 0, d).ptr, sv.f1,
                       fd.p > 0.f ? fd.scale : 1.f, sc.dF1, sc.dh, c.st, tk));
     B200ST_TRY(linear_wgrad(c, sv.h, d, sc.dF1, f, M, d, f, pre + ".w1", pre + ".b1"));
+    if (!late_flush()) B200ST_TRY(wb.flush());
     B200ST_TRY(block_ln_bwd(c, sc, sc.dh, sv.x_in, sv.mean, sv.rstd, pre, dx_out, dx_in, M, d));
     return wb.flush();
   }
@@ -914,7 +924,10 @@ static int speech_front_bwd(Ctx& c, const float* src, const float* dx0, const Fr
   void* de0 = c.act((int64_t)Mx * d);
   void* dy2 = c.act(R2 * C);
   void* dz2 = c.act(R2 * C);
-  void* dcol = c.act(R2 * 9 * C);
+  // conv2's data gradient: implicit GEMMs straight from dz2 into class-major tiles (no [rows, 9C] column gradient), or the
+  // explicit dcol = dz2 W^T + gather in conv1's backward
+  const bool implicit_dgrad = front_saves_xhat(cf) && is16(c.adt) && C == 256 && sv.F2 <= 128 && !getenv("B200ST_NO_IMPLICIT_DGRAD");
+  void* dcol = c.act(implicit_dgrad ? conv2_dgrad_implicit_elems(B, sv.T2, sv.F2, C) : R2 * 9 * C);
   void* dz1 = c.act(R1 * C);
   const int K1p = (9 * cf.in_channels + 7) / 8 * 8;
   void* col1 = c.act(R1 * K1p);
@@ -929,11 +942,12 @@ static int speech_front_bwd(Ctx& c, const float* src, const float* dx0, const Fr
     B200ST_FAIL("training without conv layer norm is not implemented");
   }
   B200ST_TRY(linear_wgrad(c, sv.col, 9 * C, dz2, C, (int)R2, 9 * C, C, "src.conv2.kernel", "src.conv2.bias"));
-  B200ST_TRY(linear_dgrad(c, dz2, C, (int)R2, C, 9 * C, "src.conv2.kernel", e0, dcol, c.adt, 9 * C));
+  if (implicit_dgrad) RUN(conv2_dgrad_implicit(dz2, c.W("src.conv2.kernel", 0, C).ptr, dcol, c.adt, B, sv.T2, sv.F2, C, c.st));
+  else B200ST_TRY(linear_dgrad(c, dz2, C, (int)R2, C, 9 * C, "src.conv2.kernel", e0, dcol, c.adt, 9 * C));
   // fused: col2im gather + ReLU' + LN' -> dz1, fbank im2col rows, db/dgamma/dbeta (xhat read back, or z1 recomputed)
   if (front_saves_xhat(cf)) {
     RUN(conv1_bwd_from_xhat(src, c.W("src.ln1.gamma", 0, C).ptr, c.W("src.ln1.beta", 0, C).ptr, sv.y1, sv.rstd1, dcol, c.adt, dz1, col1, K1p,
-                            c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F, C, c.st));
+                            c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F, C, c.st, implicit_dgrad ? 1 : 0));
   } else {
     RUN(conv1_bwd_fused(src, c.P("src.conv1.kernel"), c.P("src.conv1.bias"), c.P("src.ln1.gamma"), c.P("src.ln1.beta"), 1e-6f, sv.y1,
                         dcol, c.adt, dz1, col1, K1p, c.G("src.conv1.bias"), c.G("src.ln1.gamma"), c.G("src.ln1.beta"), B, sv.T, F,

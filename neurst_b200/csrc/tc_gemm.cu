@@ -48,6 +48,14 @@ struct TcParams {
   int atomic;
   int use_tma_store;    // epilogue writes C through per-warp smem boxes + TMA store (aligned, non-ragged tiles)
   int c_reduce;         // C += (atomic / accumulate): cp.reduce.async.bulk.tensor .add
+  // implicit transposed-convolution A operand (conv2 data gradient, see gemm_conv2_dgrad): A tile = a [conv_tu x conv_v]
+  // patch of positions x 64 channels of dY[B, T2, F2, C], shifted by the tap; k-block kb = (tap, 64-channel chunk)
+  int conv;             // 0 = off
+  int conv_ub;          // row tiles per utterance
+  int conv_tu;          // time rows per tile
+  int conv_kpc;         // k-blocks per tap (C / 64)
+  int conv_dt[4], conv_df[4], conv_wrow[4];   // per tap: time / frequency shift into dY, first row of the tap in the weight matrix
+  uint32_t conv_a_bytes;                      // bytes one A box delivers (64 ch x conv_v x conv_tu x 2)
   long long* dbg_trace; // perf experiments only: [cta][tile][8] clock64 stamps
   int dbg_epi;          // perf experiments only (B200ST_EPI_MODE): 1 = no TMA store, 2 = no smem staging either, 3 = no TMEM read
 };
@@ -242,6 +250,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.dbg_trace && kb == kb0 && tix < 8) p.dbg_trace[((int64_t)blockIdx.x * 8 + tix) * 8 + 0] = clock64();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
+          if constexpr (!A_MN && !B_MN) {
+            if (p.conv) {
+              const int tap = kb / p.conv_kpc, c0 = (kb - tap * p.conv_kpc) * BK;
+              ptx::mbar_arrive_expect_tx(full_bar(stage), p.conv_a_bytes + kBBytes);
+              ptx::tma_load_4d(sa, &tmA, full_bar(stage), c0, p.conv_df[tap], (t.m_blk % p.conv_ub) * p.conv_tu + p.conv_dt[tap],
+                               t.m_blk / p.conv_ub);
+              ptx::tma_load_4d(sb, &tmB, full_bar(stage), c0, p.conv_wrow[tap] + t.n_blk * BN, 0, 0);
+              if (++stage == stages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+          }
           ptx::mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           if (A_MN) {
 #pragma unroll
@@ -1086,7 +1105,13 @@ namespace {
 // end is RECORDED (arguments only); tc_profile_end() then replays each recorded GEMM back to back (1 warm-up + kReps timed
 // launches bracketed by one event pair, no host gap between them) and reports the per-launch average.  The buffers of the
 // step are still alive (same workspace), accumulate / reduce epilogues only add into gradients nobody reads afterwards.
-struct ProfRec { GemmArgs g; cudaStream_t stream; int bn, splitk; int group_n = 0; GemmArgs rest[3]; };   // group_n > 1: grouped weight-gradient launch (g + rest)
+// conv2 data gradient as an implicit GEMM (see conv2_dgrad_implicit): replaces the A tensor map and the k-block -> coordinates rule
+struct ConvA {
+  const void* dy; int B, T2, F2, C;     // dY [B, T2, F2, C]
+  int tu, ub, ntaps;
+  int dt[4], df[4], wrow[4];
+};
+struct ProfRec { GemmArgs g; cudaStream_t stream; int bn, splitk; int group_n = 0; GemmArgs rest[3]; bool has_conv = false; ConvA conv; };   // group_n > 1: grouped weight-gradient launch (g + rest)
 bool g_prof = false;
 std::vector<ProfRec> g_prof_recs;
 
@@ -1130,7 +1155,13 @@ TcDebug& tc_debug() {
 }
 int64_t tc_launch_count() { return g_launches; }
 
-int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
+namespace {
+int gemm_tc_impl(const GemmArgs& g, cudaStream_t stream, const ConvA* conv);
+}  // namespace
+int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) { return gemm_tc_impl(g, stream, nullptr); }
+
+namespace {
+int gemm_tc_impl(const GemmArgs& g, cudaStream_t stream, const ConvA* conv) {
   B200ST_CHECK(is16(g.A.dtype) && is16(g.B.dtype), "tcgen05 GEMM needs 16-bit (bf16 / fp16) operands");
   // measured on B200 (round 2): a kind::f16 MMA whose A and B formats differ raises an illegal-instruction fault, although
   // the instruction descriptor encodes them separately — so the library refuses mixed products up front
@@ -1169,6 +1200,7 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
       if (dbg.force_bn && c != dbg.force_bn) continue;
+      if (conv && c != 256) continue;
       if (!dbg.force_bn && c > 64 && c >= 2 * ((g.N + 63) / 64 * 64)) continue;   // do not pad N by 2x or more
       const int64_t tiles0 = batch * p.m_tiles * ceil_div(g.N, c);
       int sk_lo = splitk, sk_hi = splitk;
@@ -1250,13 +1282,40 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (tma_ok) B200ST_TRY(make_out_map(g.C, g.c_dtype, g.N, g.M, g.nb1, g.nb2, g.ldc, g.c_sb1, g.c_sb2, &tc));
 
   CUtensorMap ta, tb;
-  B200ST_TRY(make_operand_map(g.A, g.M, g.K, g.nb1, g.nb2, BM, &ta));
-  B200ST_TRY(make_operand_map(g.B, g.N, g.K, g.nb1, g.nb2, bn, &tb));
+  if (conv) {
+    B200ST_CHECK(bn == 256 && splitk == 1 && !g.A.mn_major && !g.B.mn_major && g.nb1 == 1 && g.nb2 == 1 && conv->C % BK == 0 &&
+                     g.K == conv->ntaps * conv->C && g.M == conv->B * conv->ub * BM && conv->F2 * conv->tu <= BM && conv->ntaps <= 4,
+                 "implicit conv dgrad: unsupported shape");
+    p.conv = 1; p.conv_ub = conv->ub; p.conv_tu = conv->tu; p.conv_kpc = conv->C / BK;
+    for (int i = 0; i < conv->ntaps; ++i) { p.conv_dt[i] = conv->dt[i]; p.conv_df[i] = conv->df[i]; p.conv_wrow[i] = conv->wrow[i]; }
+    p.conv_a_bytes = (uint32_t)(BK * conv->F2 * conv->tu * 2);
+    // A: dY as a 4-D tensor (C, F2, T2, B); one box = 64 channels x all F2 frequencies x tu time rows of one utterance — rows
+    // beyond the tensor (the shifted taps at the far edge) are zero-filled by the TMA unit, i.e. the convolution's border
+    EncodeTiledFn fn = get_encode_fn();
+    B200ST_CHECK(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    B200ST_CHECK((reinterpret_cast<uintptr_t>(conv->dy) & 15) == 0, "TMA operand base must be 16-byte aligned");
+    cuuint64_t dims[4] = {(cuuint64_t)conv->C, (cuuint64_t)conv->F2, (cuuint64_t)conv->T2, (cuuint64_t)conv->B};
+    cuuint64_t strides[3] = {(cuuint64_t)conv->C * 2, (cuuint64_t)conv->F2 * conv->C * 2, (cuuint64_t)conv->T2 * conv->F2 * conv->C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)conv->F2, (cuuint32_t)conv->tu, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = fn(&ta, g.A.dtype == F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(conv->dy),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) B200ST_FAIL("cuTensorMapEncodeTiled (conv dY) failed with CUresult " + std::to_string((int)r));
+    B200ST_TRY(make_operand_map(g.B, 9 * conv->C, conv->C, 1, 1, bn, &tb));      // all 9 taps of the [9C, C] weight matrix
+  } else {
+    B200ST_TRY(make_operand_map(g.A, g.M, g.K, g.nb1, g.nb2, BM, &ta));
+    B200ST_TRY(make_operand_map(g.B, g.N, g.K, g.nb1, g.nb2, bn, &tb));
+  }
 
   const int max_grid = num_sms * ctas_per_sm;
   const int grid = (int)(p.num_tiles < max_grid ? p.num_tiles : max_grid);
   ++g_launches;
-  if (g_prof) g_prof_recs.push_back(ProfRec{g, stream, bn, splitk});
+  if (g_prof) {
+    ProfRec r{g, stream, bn, splitk};
+    if (conv) { r.has_conv = true; r.conv = *conv; }
+    g_prof_recs.push_back(r);
+  }
   int rc = 0;
   switch (bn) {
     case 64: rc = launch_bn<64>(g.A.mn_major, g.B.mn_major, ta, tb, tc, p, grid, smem, stream); break;
@@ -1265,6 +1324,48 @@ int gemm_tc_bf16(const GemmArgs& g, cudaStream_t stream) {
     default: B200ST_FAIL("unsupported BN");
   }
   return rc;
+}
+}  // namespace
+
+// Data gradient of the 3x3 / stride-2 / pad-1 convolution (Conv2D#2 of AudioConv2dSubsamplingLayer,
+// neurst/layers/modalities/audio_modalities.py:96-104) as four implicit GEMMs, one per parity class (t1 & 1, f1 & 1) of the
+// input position: dA[b, t1, f1, :] = sum over the taps (kh, kw) with t1 = 2 t2 + kh - 1, f1 = 2 f2 + kw - 1 of
+// dY[b, t2, f2, :] W[kh, kw]^T — 1 tap for (even, even), 2 for the mixed classes, 4 for (odd, odd).  The A operand is read
+// straight out of dY by 4-D TMA boxes shifted by the tap (zero fill = border), so neither the [rows, 9C] column gradient
+// (737 MB at cfg-2) nor its col2im gather exist.  Output: class-major padded tiles
+//   dA[cls][b][tile][128 rows = tu x F2 positions (+ unused rows)][C],   tile = (t1 >> 1) / tu,   row = ((t1 >> 1) % tu) * F2 + (f1 >> 1)
+// which conv1's backward kernel reads back with the same arithmetic.
+int conv2_dgrad_implicit(const void* dy, const void* w16, void* da, int dtype, int B, int T2, int F2, int C, cudaStream_t stream) {
+  B200ST_CHECK(is16(dtype) && C == 256 && F2 >= 1 && F2 <= BM, "implicit conv2 dgrad: 16-bit, C == 256, F2 <= 128");
+  ConvA ca{};
+  ca.dy = dy; ca.B = B; ca.T2 = T2; ca.F2 = F2; ca.C = C;
+  ca.tu = BM / F2;
+  ca.ub = ceil_div(T2, ca.tu);
+  const int64_t cls_elems = (int64_t)B * ca.ub * BM * C;
+  for (int cls = 0; cls < 4; ++cls) {
+    const int pt = cls >> 1, pf = cls & 1;
+    // per axis: even position -> centre tap, same index; odd position -> tap 2 at the same index and tap 0 at index + 1
+    const int nt = pt ? 2 : 1, nf = pf ? 2 : 1;
+    const int kh_of[2] = {pt ? 2 : 1, 0}, dt_of[2] = {0, 1};
+    const int kw_of[2] = {pf ? 2 : 1, 0}, df_of[2] = {0, 1};
+    ca.ntaps = nt * nf;
+    for (int a = 0; a < nt; ++a)
+      for (int b2 = 0; b2 < nf; ++b2) {
+        const int i = a * nf + b2;
+        ca.dt[i] = dt_of[a]; ca.df[i] = df_of[b2]; ca.wrow[i] = (kh_of[a] * 3 + kw_of[b2]) * C;
+      }
+    GemmArgs g = gemm_defaults();
+    g.M = B * ca.ub * BM; g.N = C; g.K = ca.ntaps * C;
+    g.A = GemmOperand{dy, dtype, 0, C, 0, 0};
+    g.B = GemmOperand{w16, dtype, 0, C, 0, 0};
+    g.C = reinterpret_cast<char*>(da) + (size_t)cls * cls_elems * 2; g.c_dtype = dtype; g.ldc = C;
+    B200ST_TRY(gemm_tc_impl(g, stream, &ca));
+  }
+  return 0;
+}
+int64_t conv2_dgrad_implicit_elems(int B, int T2, int F2, int C) {
+  const int tu = BM / F2;
+  return 4 * (int64_t)B * ceil_div(T2, tu) * BM * C;
 }
 
 
@@ -1455,7 +1556,10 @@ int tc_profile_end(double* ms, double* flops, int64_t* launches) {
     GemmArgs grp_args[4];
     grp_args[0] = r.g;
     for (int i = 1; i < r.group_n; ++i) grp_args[i] = r.rest[i - 1];
-    auto run = [&]() -> int { return r.group_n > 1 ? gemm_wgrad_group(grp_args, r.group_n, st) : gemm_tc_bf16(r.g, st); };
+    auto run = [&]() -> int {
+      if (r.has_conv) return gemm_tc_impl(r.g, st, &r.conv);
+      return r.group_n > 1 ? gemm_wgrad_group(grp_args, r.group_n, st) : gemm_tc_bf16(r.g, st);
+    };
     B200ST_TRY(run());                                          // warm-up (tensor maps, instruction cache)
     B200ST_CUDA(cudaEventRecord(e0, st));
     for (int i = 0; i < kReps; ++i) B200ST_TRY(run());
