@@ -454,8 +454,12 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
     int t1 = (int)((pos / F1) % T1);
     int b = (int)(pos / ((int64_t)F1 * T1));
     const int tap_dt = lane / 3 - 1, tap_df = lane % 3 - 1;      // lanes 0..8 own one fbank tap each
-    // every global load of a position (fbank tap, xhat row, 1/sigma, <= 4 dcol rows) is issued one position ahead
-    struct Loads { Vec8<T> xh, dc[4]; float rs, xv; };
+    // every global load of a position (fbank tap, xhat row, 1/sigma, dcol rows) is issued RING-1 positions ahead: the kernel is
+    // bound by bytes in flight, not by bandwidth (ncu, round 2: 2.8 TB/s with one position ahead) — the implicit variant loads
+    // one gradient row instead of four and spends the freed registers on a deeper ring
+    constexpr int NDC = IMPLICIT ? 1 : 4;
+    constexpr int RING = IMPLICIT ? 4 : 2;
+    struct Loads { Vec8<T> xh, dc[NDC]; float rs, xv; };
     auto issue = [&](int64_t p, int bb, int tt1, int ff1, Loads& L) {
       L.xv = 0.f;
       if (lane < 9) {
@@ -464,41 +468,36 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
       }
       L.xh.load(xhat + p * C + 8 * lane);
       L.rs = __ldg(rstd + p);
-      if (IMPLICIT) {
+      if constexpr (IMPLICIT) {
         const int cls = ((tt1 & 1) << 1) | (ff1 & 1), u = tt1 >> 1, v = ff1 >> 1;
         const int64_t row = (((int64_t)cls * B + bb) * ub + u / tu) * 128 + (u % tu) * F2 + v;
         L.dc[0].load(dcol + row * C + 8 * lane);
-        return;
-      }
-      // col2im: t1 even -> kh = 1 ; t1 odd -> kh in {0, 2} (same along f); slot = 2 * a + c2
-      const int kh0 = (tt1 & 1) ? 0 : 1, kw0 = (ff1 & 1) ? 0 : 1;
+      } else {
+        // col2im: t1 even -> kh = 1 ; t1 odd -> kh in {0, 2} (same along f); slot = 2 * a + c2
+        const int kh0 = (tt1 & 1) ? 0 : 1, kw0 = (ff1 & 1) ? 0 : 1;
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 2; ++a) {
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          const int kh = kh0 + 2 * a, kw = kw0 + 2 * c2;
-          const int t2 = (tt1 + 1 - kh) >> 1, f2 = (ff1 + 1 - kw) >> 1;
-          const bool ok = (a == 0 || (tt1 & 1)) && (c2 == 0 || (ff1 & 1)) && t2 < T2 && f2 < F2;
-          if (ok) L.dc[2 * a + c2].load(dcol + ((((int64_t)bb * T2 + t2) * F2 + f2) * 9 + kh * 3 + kw) * C + 8 * lane);
-          else L.dc[2 * a + c2].zero();
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int kh = kh0 + 2 * a, kw = kw0 + 2 * c2;
+            const int t2 = (tt1 + 1 - kh) >> 1, f2 = (ff1 + 1 - kw) >> 1;
+            const bool ok = (a == 0 || (tt1 & 1)) && (c2 == 0 || (ff1 & 1)) && t2 < T2 && f2 < F2;
+            if (ok) L.dc[2 * a + c2].load(dcol + ((((int64_t)bb * T2 + t2) * F2 + f2) * 9 + kh * 3 + kw) * C + 8 * lane);
+            else L.dc[2 * a + c2].zero();
+          }
         }
       }
     };
-    Loads cur, nxt;
-    issue(pos, b, t1, f1, cur);
-    for (; pos < pos_end; ++pos) {
-      if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
-      if (pos + 1 < pos_end) issue(pos + 1, b, t1, f1, nxt);
-      float xh[8], d[8], t8[8];
+    auto process = [&](int64_t pp, const Loads& cur) {
+      float xh[8], d[8];
       cur.xh.get(xh);
       cur.dc[0].get(d);
-      if (!IMPLICIT) {
 #pragma unroll
-        for (int k = 1; k < 4; ++k) {
-          cur.dc[k].get(t8);
+      for (int k = 1; k < NDC; ++k) {
+        float t8[8];
+        cur.dc[k].get(t8);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] += t8[i];
-        }
+        for (int i = 0; i < 8; ++i) d[i] += t8[i];
       }
       const float rs = cur.rs;
       float c1 = 0.f, c2s = 0.f;
@@ -514,9 +513,31 @@ __global__ void __launch_bounds__(256, 2) conv1_bwd_xhat_c256_kernel(
       c1 *= (1.0f / C); c2s *= (1.0f / C);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { d[i] = rs * (d[i] * greg[i] - c1 - xh[i] * c2s); a_db[i] += d[i]; }
-      st8<T>(dz1 + pos * C + 8 * lane, d);
-      if (lane < K1p) col1[pos * K1p + lane] = from_f32<T>(lane < 9 ? cur.xv : 0.f);
-      cur = nxt;
+      st8<T>(dz1 + pp * C + 8 * lane, d);
+      if (lane < K1p) col1[pp * K1p + lane] = from_f32<T>(lane < 9 ? cur.xv : 0.f);
+    };
+    // issue cursor (position whose loads are issued next) runs RING-1 positions ahead of the compute cursor `pos`
+    int64_t ipos = pos;
+    int ib = b, it1 = t1, if1 = f1;
+    auto issue_next = [&](Loads& L) {
+      if (ipos < pos_end) {
+        issue(ipos, ib, it1, if1, L);
+        ++ipos;
+        if (++if1 == F1) { if1 = 0; if (++it1 == T1) { it1 = 0; ++ib; } }
+      }
+    };
+    Loads ring[RING];
+#pragma unroll
+    for (int j = 0; j < RING - 1; ++j) issue_next(ring[j]);
+    while (pos < pos_end) {
+#pragma unroll
+      for (int j = 0; j < RING; ++j) {
+        if (pos < pos_end) {
+          issue_next(ring[(j + RING - 1) % RING]);
+          process(pos, ring[j]);
+          ++pos;
+        }
+      }
     }
   }
 #pragma unroll
