@@ -279,11 +279,21 @@ __global__ void __launch_bounds__(256, 2) conv1_fwd_c256_kernel(const float* __r
     }
     return v;
   };
-  float xv_next = load_tap(b, t1, f1);
-  for (; pos < pos_end; ++pos) {
-    const float xv = xv_next;
-    if (++f1 == F1) { f1 = 0; if (++t1 == T1) { t1 = 0; ++b; } }
-    if (pos + 1 < pos_end) xv_next = load_tap(b, t1, f1);        // next position's taps: in flight during the math
+  // the taps of the next RING-1 positions are in flight during the math of the current one (one position ahead left the
+  // warps waiting on L2: 203 us for 0.28 GB of traffic, ncu round 2)
+  constexpr int RING = 4;
+  int64_t ipos = pos;
+  int ib = b, it1 = t1, if1 = f1;
+  auto issue_next = [&]() {
+    float v = 0.f;
+    if (ipos < pos_end) {
+      v = load_tap(ib, it1, if1);
+      ++ipos;
+      if (++if1 == F1) { if1 = 0; if (++it1 == T1) { it1 = 0; ++ib; } }
+    }
+    return v;
+  };
+  auto process = [&](int64_t pp, float xv) {
     float z[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) z[i] = breg[i];
@@ -304,12 +314,25 @@ __global__ void __launch_bounds__(256, 2) conv1_fwd_c256_kernel(const float* __r
     if (SAVE) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) z[i] *= rstd;
-      if (lane == 0) rstd_out[pos] = rstd;
+      if (lane == 0) rstd_out[pp] = rstd;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) z[i] = fmaxf(fmaf(z[i] * rstd, greg[i], bereg[i]), 0.f);
     }
-    st8<T>(y + pos * C + 8 * lane, z);
+    st8<T>(y + pp * C + 8 * lane, z);
+  };
+  float ring[RING];
+#pragma unroll
+  for (int j = 0; j < RING - 1; ++j) ring[j] = issue_next();
+  while (pos < pos_end) {
+#pragma unroll
+    for (int j = 0; j < RING; ++j) {
+      if (pos < pos_end) {
+        ring[(j + RING - 1) % RING] = issue_next();
+        process(pos, ring[j]);
+        ++pos;
+      }
+    }
   }
 }
 
