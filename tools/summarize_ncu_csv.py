@@ -32,7 +32,7 @@ print("launches %d   total gpu time %.1f us (serialised, cold-cache: shares are 
 for k, (n, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-92s n=%5d total=%9.1f us avg=%8.1f us share=%.3f%s" % (k, n, t, t / n, t / tot, ("  dram=%.1f MB" % (b / 1e6)) if b else ""))
 if out_json and match:
-    sel = [(n, t, b) for k, (n, t, b) in agg.items() if match in k]
+    sel = [(n, t, b) for k, (n, t, b) in agg.items() if re.search(match, k)]      # --match is a regular expression
     json.dump({"kernel": match, "launches": sum(x[0] for x in sel), "time_us": sum(x[1] for x in sel),
                "dram_bytes_total": sum(x[2] for x in sel), "all_kernels_time_us": tot,
                "share_of_step": sum(x[1] for x in sel) / tot, "source": path}, open(out_json, "w"), indent=1)
