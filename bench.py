@@ -155,6 +155,29 @@ def cpu_reference_step_time(B, T, L, steps, warmup, threads):
     return times[len(times) // 2], float(loss.detach())
 
 
+def cpu_reference_forward_time(B, T, L, steps, warmup, threads):
+    """The UNMODIFIED reference `neurst_pt` SpeechTransformer (staged under oracle/_ref by oracle/build_ref.py), forward only
+    (its autograd does not run on this torch), training mode (dropout on), same synthetic batch."""
+    import torch
+    from oracle import build_ref
+    from oracle import restatement as R
+    torch.set_num_threads(threads)
+    cfg = dict(R.CONFIGS["speech_transformer_s"])
+    model = build_ref.reference_speech_transformer(cfg, cfg["vocab"])
+    from neurst_b200.trainer import synthetic_batch
+    batch = synthetic_batch(B, T, L, cfg["vocab"], seed=1234)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            logits = model({"src": batch["src"].clone(), "src_length": batch["src_length"], "trg_input": batch["trg_input"]}, is_training=True)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    times.sort()
+    return times[len(times) // 2], float(logits.float().abs().mean())
+
+
 def cpu_threads():
     """Threads of the CPU arm.  The oracle's ops at the bounded sample size stop scaling near 16 intra-op threads, and
     on a shared host more OpenMP threads than free cores is catastrophically slow (spin-waits) — measured: 8 threads
@@ -163,11 +186,11 @@ def cpu_threads():
     return int(env) if env else max(1, min(len(os.sched_getaffinity(0)), 16))
 
 
-def cpu_sample(B, T, L, steps, warmup, threads, timeout_s):
+def cpu_sample(B, T, L, steps, warmup, threads, timeout_s, which="--cpu-worker"):
     """Runs the oracle sample in a child process (exact PID, killed on timeout) so that the bench always terminates."""
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), OMP_WAIT_POLICY="PASSIVE",
                KMP_BLOCKTIME="0", CUDA_VISIBLE_DEVICES="")
-    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "%d,%d,%d,%d,%d,%d" % (B, T, L, steps, warmup, threads)]
+    cmd = [sys.executable, os.path.abspath(__file__), which, "%d,%d,%d,%d,%d,%d" % (B, T, L, steps, warmup, threads)]
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
     try:
         out, _ = proc.communicate(timeout=timeout_s)
@@ -190,7 +213,14 @@ def cpu_baseline_object(steps, warmup):
         if r is not None:
             sample = "oracle port (fp32 torch-CPU restatement of the reference graph) fwd+bwd, dropout on, B=%d x T=%d frames " \
                      "per step, median of %d step(s) after %d warm-up" % (B, Tn, steps, warmup)
-            return {"value": B * Tn / r["sec"], "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}, r["sec"], (B, Tn, Ln)
+            obj = {"value": B * Tn / r["sec"], "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
+            # beside it: the unmodified reference itself, for the part of the step it can run (forward only)
+            rf = cpu_sample(B, Tn, Ln, steps, warmup, threads, 90, which="--cpu-ref-worker")
+            if rf is not None and rf.get("sec"):
+                obj["reference_forward"] = {"value": B * Tn / rf["sec"], "unit": "frames/s (forward only)", "kind": "reference", "cores": threads,
+                                            "sample": "unmodified reference neurst_pt.SpeechTransformer.forward(is_training=True) staged under oracle/_ref "
+                                                      "(oracle/build_ref.py), same batch; the reference has no runnable backward"}
+            return obj, r["sec"], (B, Tn, Ln)
     return None, None, None
 
 
@@ -213,6 +243,15 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_ref_worker(spec):
+    B, T, L, steps, warmup, threads = [int(x) for x in spec.split(",")]
+    try:
+        sec, chk = cpu_reference_forward_time(B, T, L, steps, warmup, threads)
+        print(json.dumps({"sec": sec, "check": chk}), flush=True)
+    except Exception as e:       # no staged reference on this box: the port number stands alone
+        print(json.dumps({"sec": None, "error": str(e)[:200]}), flush=True)
 
 
 def cpu_worker(spec):
@@ -507,7 +546,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),
     }
-    # roofline of the dominant kernel (tc_gemm_kernel: ~280 launches, ~55 % of the step): algorithmic FLOPs of those
+    # roofline of the dominant kernel family (tc_gemm_kernel / tc_wgrad_group_kernel: ~160 launches, ~42 % of the step): algorithmic FLOPs of those
     # launches / their durations: the GEMMs of one eagerly launched step are recorded and each is replayed back to back
     # inside the library with CUDA events around the repetitions (a graph replay cannot be bracketed per kernel).  `traffic` = DRAM bytes per launch from the committed ncu pass
     # (profiles/r02_gemm_traffic.json, same command), averaged like `achieved`.
@@ -526,7 +565,7 @@ def run_gpu(args):
             continue
     if gemm and gemm["ms"] > 0:
         g_tf = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05, all instantiations)", "achieved": g_tf,
+        line["roofline"] = {"bound": "tensor", "kernel": "tc_gemm_kernel (all instantiations) + tc_wgrad_group_kernel (tcgen05 GEMMs outside the fused FFN / attention kernels)", "achieved": g_tf,
                             "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": g_tf / peaks["tflops_sustained"],
                             "peak_burst": peaks["tflops_burst"], "frac_of_burst_peak": g_tf / peaks["tflops_burst"],
                             "traffic": traffic, "peak_source": peaks["source"], "launches_per_step": gemm["launches"],
@@ -556,6 +595,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-worker", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-ref-worker", default="", help=argparse.SUPPRESS)
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the CUDA graph")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"],
                     help="fp16 = the reference's mixed_float16 (default: logits within 3.2e-3 of the fp64 oracle); bf16; fp32 parity mode")
@@ -563,6 +603,9 @@ def main():
                     help="cfg2 = BASELINE headline [32,1000,80]; cfg3 / cfg3w = [8|64,1500,80]; cfg4 = speech_transformer_m ragged buckets; "
                          "decode = cfg-5 greedy decode")
     args = ap.parse_args()
+    if args.cpu_ref_worker:
+        cpu_ref_worker(args.cpu_ref_worker)
+        return
     if args.cpu_worker:
         cpu_worker(args.cpu_worker)
         return

@@ -135,3 +135,46 @@ def test_specaugment_masks_follow_the_reference_rule():
     assert int(t_rows[0].sum()) <= 2 * 100 and int(changed.any(1)[0].sum()) <= 80
     mean0 = float(src[0, :, :, 0].mean())
     assert abs(float(out[0][changed[0]].mean()) - mean0) < 1e-5                            # filled with the utterance mean
+
+
+def test_staged_reference_copy_is_unmodified_and_runs():
+    """oracle/_ref (oracle/build_ref.py): every staged file is byte-identical to the reference's, and the staged tree —
+    the one that travels to the GPU box for bench.py's `cpu_baseline.reference_forward` — reproduces the oracle forward."""
+    import hashlib
+    import json
+    import subprocess
+    import sys
+    from oracle import build_ref
+    root = build_ref.build()
+    if root is None:
+        pytest.skip("no staged reference and no /root/reference")
+    man = json.load(open(os.path.join(root, "MANIFEST.json")))["files"]
+    assert len(man) > 20 and "neurst_pt/models/speech_transformer.py" in man
+    for rel, digest in man.items():
+        assert hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest() == digest
+        if os.path.isdir(REF):
+            assert hashlib.sha256(open(os.path.join(REF, rel), "rb").read()).hexdigest() == digest, rel
+    code = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+os.environ["NEURST_REFERENCE_SRC"] = "/nonexistent"          # force the staged tree
+from oracle import build_ref, restatement as R
+from neurst_b200 import checkpoints as CK
+cfg = dict(model="speech", d=16, heads=2, enc_layers=2, dec_layers=2, ffn=24, channels=8, feat=80, in_channels=1, vocab=20)
+import importlib; importlib.reload(build_ref)
+model = build_ref.reference_speech_transformer(cfg, 20)
+import neurst_pt
+assert os.path.realpath(neurst_pt.__file__).startswith(os.path.realpath(build_ref.DEST)), neurst_pt.__file__
+P = R.init_params(cfg, seed=5, random_bias=True)
+CK.to_reference_pt(P, model)
+g = torch.Generator().manual_seed(0)
+src = torch.randn(2, 41, 80, 1, generator=g); lens = torch.tensor([41, 30]); ti = torch.randint(0, 17, (2, 5), generator=g)
+with torch.no_grad():
+    ref = model({"src": src, "src_length": lens, "trg_input": ti}, is_training=False)
+mine = R.speech_transformer_forward(P, cfg, src, lens, ti)
+print("MAXDIFF", float((ref - mine).abs().max()))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    diff = float(out.stdout.strip().split("MAXDIFF")[-1])
+    assert diff < 1e-4, diff
