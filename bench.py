@@ -315,6 +315,9 @@ def run_decode(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     lib.load()
     V, T, steps = 8192, 2000, 200
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_w0 = time.time()
     hp = dict(speech_transformer_hparams("speech_transformer_s")["model.params"])
     tm = {"vocab_size": V, "eos_id": V - 1, "bos_id": V - 2, "unk_id": V - 3}
     out = {}
@@ -353,6 +356,8 @@ def run_decode(args):
         out[dtype] = dict(encode_ms=enc_ms, decode_ms=dec_ms, us_per_token=dec_ms * 1e3 / steps, tokens=int(ln[0]),
                           weights="16-bit shadow" if shadow else "fp32 master", mode=mode,
                           us_per_token_graph_replay=g0.elapsed_time(g1) * 1e3 / steps)
+    sampler.mark(t_w0, time.time())
+    sampler.stop()
     wbytes = 10.8e6          # decoder + tied embedding parameters read per token
     peaks = load_peaks()
     best = out["fp16"]
@@ -368,6 +373,7 @@ def run_decode(args):
                                  "K/V); floor %.1f us/token" % floor_us},
             "e2e": {"value": steps / ((best["encode_ms"] + best["decode_ms"]) * 1e-3), "unit": "tokens/s (encoder pass + cache "
                     "build + 200 steps + ids D2H)", "h2d_bytes_per_step": T * 80 * 4, "d2h_bytes_per_step": steps * 8},
+            "clocks": sampler.summary(),
             "gpu_launches": 2}
     print(json.dumps(line), flush=True)
 

@@ -767,7 +767,7 @@ static int conv1_fwd_launch(const float* src, const float* w, const float* b, co
   if (vec && C == 256 && Cin == 1 && (use_ln || rstd_out) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
       ((reinterpret_cast<uintptr_t>(b) & 15) == 0) && (rstd_out || (((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0))) {
     const int grid1 = pick_grid(npos, 8 * 16, 148 * 2);
-    static const bool f2 = getenv("B200ST_CONV1_FFMA2") != nullptr;      // packed fp32x2 FMAs (same rounding: fma.rn per element)
+    static const bool f2 = getenv("B200ST_NO_CONV1_FFMA2") == nullptr;   // packed fp32x2 FMAs (same rounding: fma.rn per element; 6.155 vs 6.173 ms step)
     if (rstd_out && f2) DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_c256_kernel<TT, true, true>, grid1, 256, 0, s, src, w, b, gamma, beta, eps, (TT*)y1, rstd_out, B, T, F, T1, F1)));
     else if (rstd_out) DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_c256_kernel<TT, true>, grid1, 256, 0, s, src, w, b, gamma, beta, eps, (TT*)y1, rstd_out, B, T, F, T1, F1)));
     else DISPATCH_DTYPE(y_dtype, TT, (launch_pdl(conv1_fwd_c256_kernel<TT, false>, grid1, 256, 0, s, src, w, b, gamma, beta, eps, (TT*)y1, rstd_out, B, T, F, T1, F1)));
