@@ -30,13 +30,8 @@ def io_lib():
     """ctypes handle of libb200st_io.so (built in-tree with gcc on first use)."""
     global _LIB
     if _LIB is None:
-        import sys
-        sys.path.insert(0, os.path.join(_HERE, "csrc"))
-        try:
-            import build as _build
-            path = _build.build_io()
-        finally:
-            sys.path.pop(0)
+        from neurst_b200.csrc import build as _build
+        path = _build.build_io()
         lib = C.CDLL(path)
         lib.b200st_crc32c.restype = C.c_uint32
         lib.b200st_crc32c.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
