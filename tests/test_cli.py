@@ -144,3 +144,21 @@ def test_train_resume_predict_through_the_entry(tmp_path):
     lines = open(out, encoding="utf-8").read().split("\n")
     assert len(lines) == 71 and all(all(t.startswith("tok") or t == "<UNK>" for t in l.split()) for l in lines[:-1])
     torch.cuda.synchronize()
+
+
+def test_rank_shards_are_disjoint_and_complete(tmp_path):
+    """Each rank streams its own TFRecord files (dataset_utils.load_tfrecords auto-shard under Horovod); with fewer files than
+    ranks every rank reads everything."""
+    n = _write_dataset(tmp_path, n_shards=4, per_shard=9)
+    y = _write_yaml(tmp_path, data=str(tmp_path / "train.tfrecords"))
+    plan = cli.resolve(cli.load_config([y], [("task.params.batch_size", 3000), ("task.params.max_src_len", 400),
+                                             ("task.params.max_trg_len", 24)]))
+    seen = []
+    for rank in range(2):
+        _, ex = cli._examples(plan, rank, 2, training=False)
+        seen.append([int(e["audio_length"]) for e in ex])
+    assert len(seen[0]) == len(seen[1]) == 18 and len(seen[0]) + len(seen[1]) == n
+    _, ex = cli._examples(plan, 0, 1, training=False)
+    assert sorted(seen[0] + seen[1]) == sorted(int(e["audio_length"]) for e in ex)
+    _, ex = cli._examples(plan, 3, 8, training=False)              # 4 files, 8 ranks: no sharding
+    assert sum(1 for _ in ex) == n
