@@ -259,7 +259,7 @@ def _examples(plan, rank, world, training):
 def train(plan):
     from neurst_b200 import checkpoints as CK
     from neurst_b200.trainer import DataParallelTrainer, HostPipeline
-    world, rank, _ = _dist_setup()
+    world, rank, local = _dist_setup()
     model = _build_model(plan)
     start_path, start_step = latest_checkpoint(plan["model_dir"])
     if start_path:
@@ -279,21 +279,27 @@ def train(plan):
     trainer.broadcast_parameters()
     task, examples = _examples(plan, rank, world, training=True)
     gen = torch.Generator().manual_seed(plan["seed"] + rank)
-    batches = (per_rank[0] for per_rank in task.train_batches(examples, generator=gen, pin=True))
+    from neurst_b200.data import Prefetcher
+    import itertools
     last = None
     micro_target = (plan["train_steps"] - start_step) * plan["update_cycle"]
     if micro_target > 0:
-        import itertools
-        losses = HostPipeline(trainer).run(itertools.islice(batches, micro_target), seed0=start_step * plan["update_cycle"] + 1)
-        saved_at = start_step
-        for loss in losses:
-            if loss is not None:
-                last = loss
-            step = trainer.global_step
-            if rank == 0 and step > saved_at and step % plan["save_checkpoint_steps"] == 0:
-                torch.cuda.synchronize()
-                save_checkpoint(model.runtime, plan["model_dir"], step, plan["max_to_keep"])
-                saved_at = step
+        # reading, parsing, padding and pinning of the next batches run in a background thread (tf.data prefetch's role)
+        batches = Prefetcher(itertools.islice((per_rank[0] for per_rank in task.train_batches(examples, generator=gen, pin=True)),
+                                              micro_target), depth=4, init=lambda: torch.cuda.set_device(local))
+        try:
+            losses = HostPipeline(trainer).run(batches, seed0=start_step * plan["update_cycle"] + 1)
+            saved_at = start_step
+            for loss in losses:
+                if loss is not None:
+                    last = loss
+                step = trainer.global_step
+                if rank == 0 and step > saved_at and step % plan["save_checkpoint_steps"] == 0:
+                    torch.cuda.synchronize()
+                    save_checkpoint(model.runtime, plan["model_dir"], step, plan["max_to_keep"])
+                    saved_at = step
+        finally:
+            batches.close()
     torch.cuda.synchronize()
     if rank == 0 and trainer.global_step > start_step:
         save_checkpoint(model.runtime, plan["model_dir"], trainer.global_step, plan["max_to_keep"])

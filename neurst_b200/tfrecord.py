@@ -60,7 +60,9 @@ def masked_crc32c(data):
 def read_records(path, verify=2):
     """Yields the payload of every record of one file as a uint8 numpy view of the file image (one read of the whole file,
     like the reference's TFRecordDataset(buffer_size=128 MB)).  verify: 0 none / 1 length CRCs / 2 length + payload CRCs."""
-    img = np.fromfile(path, dtype=np.uint8)
+    if os.path.getsize(path) == 0:
+        return
+    img = np.memmap(path, dtype=np.uint8, mode="r")      # pages stream in as the index / checksum pass walks the file
     lib = io_lib()
     n = int(lib.b200st_tfrecord_index(img.ctypes.data, img.size, None, None, 0, int(verify)))
     if n < 0:

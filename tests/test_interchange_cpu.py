@@ -178,3 +178,28 @@ print("MAXDIFF", float((ref - mine).abs().max()))
     assert out.returncode == 0, out.stderr[-2000:]
     diff = float(out.stdout.strip().split("MAXDIFF")[-1])
     assert diff < 1e-4, diff
+
+
+def test_prefetcher_order_errors_and_shutdown():
+    import threading
+    seen = []
+    p = D.Prefetcher(iter(range(20)), depth=2, init=lambda: seen.append(threading.current_thread().name))
+    assert list(p) == list(range(20)) and len(seen) == 1 and seen[0] != threading.current_thread().name
+
+    def bad():
+        yield 1
+        raise ValueError("boom")
+    q = D.Prefetcher(bad())
+    assert next(q) == 1
+    with pytest.raises(ValueError):
+        next(q)
+
+    def endless():
+        i = 0
+        while True:
+            yield torch.full((4,), float(i))
+            i += 1
+    r = D.Prefetcher(endless(), depth=3)
+    assert [float(next(r)[0]) for _ in range(5)] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    r.close()
+    assert not r._t.is_alive()
