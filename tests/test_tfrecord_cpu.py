@@ -205,3 +205,20 @@ def test_audio_tfrecord_dataset_and_speech_to_text_batches(tmp_path):
     assert raw.status["transcript"] == "raw" and next(raw.build_iterator()())["transcript"] == "hello world 0"
     with pytest.raises(RuntimeError):
         task.preprocess_fn(raw.status)
+
+
+
+def test_specaugment_in_batches_is_reproducible(tmp_path):
+    rng = np.random.default_rng(9)
+    _audio_records(tmp_path / "train.tfrecords-00000-of-00001", 200, rng)
+    ds = R.AudioTFRecordDataset({"data_path": str(tmp_path / "train.tfrecords")})
+
+    def run(seed):
+        task = D.SpeechToText({"pad_id": 0, "bos_id": 1, "eos_id": 2}, max_src_len=640, max_trg_len=24, batch_size_per_gpu=4000,
+                              frame_transcript_ratio=30, specaug="SM")
+        g = torch.Generator().manual_seed(seed)
+        return list(task.train_batches(ds.build_iterator(map_func=task.preprocess_fn(ds.status))(), generator=g))
+    a, b, c = run(4), run(4), run(5)
+    assert len(a) == len(b) == len(c) > 2
+    assert all(torch.equal(x[0]["src"], y[0]["src"]) for x, y in zip(a, b))
+    assert any(not torch.equal(x[0]["src"], y[0]["src"]) for x, y in zip(a, c))
