@@ -112,15 +112,22 @@ class FrameBudgetBucketer:
 
     def _pad(self, group, key, pad_id, feature_dim):
         T, L, B = self.boundaries[key[0]], self.trg_pairs[key[0]][key[1]], len(group)
-        flat = torch.empty(B, T * feature_dim)            # rows filled with contiguous copies (10x faster than strided 4-D slices);
-        trg = torch.full((B, L), int(pad_id), dtype=torch.long)      # every byte is written exactly once: data, then the zero tail
+        flat = torch.empty(B, T * feature_dim)
+        trg = torch.full((B, L), int(pad_id), dtype=torch.long)
         sl, tl = torch.zeros(B, dtype=torch.long), torch.zeros(B, dtype=torch.long)
+        rows = []
         for j, ex in enumerate(group):
             n, l = ex["audio"].shape[0], ex["transcript"].numel()
-            flat[j, :n * feature_dim] = ex["audio"].reshape(-1)
-            flat[j, n * feature_dim:] = 0.0
+            a = ex["audio"]
+            rows.append(a if (a.dtype == torch.float32 and a.is_contiguous()) else a.to(torch.float32).contiguous())
             trg[j, :l] = ex["transcript"]
             sl[j], tl[j] = n, l
+        # padded_batch in C (libb200st_io: one memcpy + one memset per row, outside the GIL): every byte written exactly once
+        import ctypes as C
+        from neurst_b200.tfrecord import io_lib
+        ptrs = (C.c_void_p * B)(*[r.data_ptr() for r in rows])
+        lens = (C.c_int64 * B)(*[r.numel() for r in rows])
+        io_lib().b200st_pad_rows_f32(flat.data_ptr(), T * feature_dim, ptrs, lens, B)
         return dict(src=flat.view(B, T, feature_dim, 1), src_length=sl, trg=trg, trg_length=tl)
 
 

@@ -41,7 +41,15 @@ def io_lib():
         lib.b200st_tfrecord_index.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         lib.b200st_tfrecord_frame.restype = None
         lib.b200st_tfrecord_frame.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
-        if lib.b200st_io_version() != 1:
+        lib.b200st_crc32c_table.restype = C.c_uint32
+        lib.b200st_crc32c_table.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
+        lib.b200st_example_lookup.restype = C.c_int
+        lib.b200st_example_lookup.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200st_decode_varints.restype = C.c_int64
+        lib.b200st_decode_varints.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64]
+        lib.b200st_pad_rows_f32.restype = None
+        lib.b200st_pad_rows_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
+        if lib.b200st_io_version() != 2:
             raise RuntimeError("libb200st_io.so does not match this binding")
         _LIB = lib
     return _LIB
@@ -196,6 +204,51 @@ def _feature(buf, a, b):
     return kind, val
 
 
+class FeatureLookup:
+    """Native lookup of a fixed set of features in serialized Examples (b200st_example_lookup): one C call per record instead
+    of a Python walk over the protobuf fields; float lists come back as zero-copy views, id lists are decoded in C."""
+
+    def __init__(self, name_to_features):
+        self.names = list(name_to_features)
+        self.kinds = [name_to_features[k] for k in self.names]
+        n = len(self.names)
+        self._keys = (C.c_char_p * n)(*[k.encode("utf-8") for k in self.names])
+        self._kind = np.zeros(n, np.int32)
+        self._off, self._len, self._cnt = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        self._lib = io_lib()
+
+    _CODE = {1: "bytes", 2: "float", 3: "int64"}
+
+    def __call__(self, rec):
+        """rec: uint8 numpy view of one record -> {name: value} like `to_dense(parse_example(rec), schema)`; None when the
+        record stores a list unpacked (the caller falls back to the general decoder)."""
+        rc = self._lib.b200st_example_lookup(rec.ctypes.data, rec.size, self._keys, len(self.names), self._kind.ctypes.data,
+                                             self._off.ctypes.data, self._len.ctypes.data, self._cnt.ctypes.data)
+        if rc != 0:
+            raise TFRecordError("malformed tf.train.Example")
+        out = {}
+        for i, name in enumerate(self.names):
+            want, got = self.kinds[i], int(self._kind[i])
+            a, ln, cnt = int(self._off[i]), int(self._len[i]), int(self._cnt[i])
+            if got == 0:
+                out[name] = [] if want == "bytes" else np.empty(0, np.float32 if want == "float" else np.int64)
+                continue
+            if self._CODE[got] != want:
+                raise TFRecordError("feature %r is stored as %s_list, the schema asks for %s" % (name, self._CODE[got], want))
+            if cnt < 0 or (got == 1 and cnt != 1):
+                return None
+            if got == 2:
+                out[name] = np.frombuffer(rec[a:a + ln], dtype="<f4")
+            elif got == 3:
+                v = np.empty(cnt, np.int64)
+                if self._lib.b200st_decode_varints(rec.ctypes.data + a, ln, v.ctypes.data, cnt) != cnt:
+                    raise TFRecordError("malformed packed varint list")
+                out[name] = v
+            else:
+                out[name] = [bytes(rec[a:a + ln])]
+        return out
+
+
 def parse_example(payload):
     """Serialized tf.train.Example -> {name: (kind, value)} with kind in {'bytes','float','int64', None (empty feature)}."""
     buf = payload if isinstance(payload, np.ndarray) else np.frombuffer(bytes(payload), np.uint8)
@@ -304,6 +357,7 @@ def load_tfrecords(file_path, name_to_features=None, feature_name_mapping=None, 
     files = glob_tfrecords(file_path)
     if num_shards > 1:
         files = files[sharding_index::num_shards]
+    lookup = FeatureLookup(name_to_features) if name_to_features is not None else None
     pending = iter(files)
     slots = []
     for _ in range(cycle_length):
@@ -326,7 +380,11 @@ def load_tfrecords(file_path, name_to_features=None, feature_name_mapping=None, 
         if name_to_features is None:
             yield rec
             continue
-        el = to_dense(parse_example(rec), name_to_features, feature_name_mapping)
+        fast = lookup(rec)
+        if fast is None:           # a list stored unpacked / several bytes values: general decoder
+            el = to_dense(parse_example(rec), name_to_features, feature_name_mapping)
+        else:
+            el = {(feature_name_mapping or {}).get(k, k): v for k, v in fast.items()}
         if isinstance(auxiliary_elements, dict):
             el.update(auxiliary_elements)
         yield el if map_func is None else map_func(el)

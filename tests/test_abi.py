@@ -27,7 +27,8 @@ def test_io_library_exports_every_declared_symbol():
     from neurst_b200.csrc import build as B
     header = open(os.path.join(ROOT, "include", "b200st_io.h")).read()
     declared = set(re.findall(r"\b(b200st_[a-z0-9_]+)\s*\(", header))
-    assert declared == {"b200st_io_version", "b200st_crc32c", "b200st_crc32c_mask", "b200st_tfrecord_index", "b200st_tfrecord_frame"}
+    assert declared == {"b200st_io_version", "b200st_crc32c", "b200st_crc32c_table", "b200st_crc32c_mask", "b200st_tfrecord_index",
+                        "b200st_tfrecord_frame", "b200st_example_lookup", "b200st_decode_varints", "b200st_pad_rows_f32"}
     lib = ctypes.CDLL(B.build_io())
     for sym in declared:
         assert hasattr(lib, sym), sym

@@ -222,3 +222,58 @@ def test_specaugment_in_batches_is_reproducible(tmp_path):
     assert len(a) == len(b) == len(c) > 2
     assert all(torch.equal(x[0]["src"], y[0]["src"]) for x, y in zip(a, b))
     assert any(not torch.equal(x[0]["src"], y[0]["src"]) for x, y in zip(a, c))
+
+
+def test_native_lookup_varints_padding_and_hardware_crc(tmp_path):
+    import ctypes as C
+    lib = R.io_lib()
+    rng = np.random.default_rng(3)
+    # the SSE4.2 path and the portable table path agree (odd alignments and lengths)
+    blob = rng.integers(0, 256, 70001, dtype=np.uint8)
+    for a, n in ((0, 0), (1, 7), (3, 64), (5, 1001), (0, 70001), (7, 69990)):
+        view = blob[a:a + n]
+        assert lib.b200st_crc32c(0, view.ctypes.data, n) == lib.b200st_crc32c_table(0, view.ctypes.data, n) == R.crc32c(view.tobytes())
+    # records written by TensorFlow: native lookup == general decoder
+    for g in GOLD["records"]:
+        raw = np.frombuffer(bytes.fromhex(g["framed_hex"]), np.uint8)
+        rec = raw[12:-4]
+        fast = R.FeatureLookup({"feature": R.VarLenInt64, "label": R.VarLenInt64, "absent": R.VarLenFloat})(rec)
+        assert fast["feature"].tolist() == g["ids"]["feature"] and fast["label"].tolist() == g["ids"]["label"] and fast["absent"].size == 0
+    # random examples: floats zero-copy, negative / 10-byte varints, single bytes value, empty lists, schema mismatch, fall-backs
+    schema = {"audio": R.VarLenFloat, "transcript": R.VarLenInt64, "uuid": R.VarLenString, "src_lang": R.VarLenString, "none": R.VarLenInt64}
+    look = R.FeatureLookup(schema)
+    for _ in range(20):
+        n = int(rng.integers(0, 300))
+        ids = rng.integers(-2 ** 62, 2 ** 62, int(rng.integers(0, 40))).astype(np.int64)
+        ex = {"audio": rng.standard_normal(n * 80).astype(np.float32), "transcript": ids, "uuid": "u%d" % n, "src_lang": "en",
+              "other": np.arange(5)}
+        rec = np.frombuffer(R.encode_example(ex), np.uint8)
+        fast, slow = look(rec), R.to_dense(R.parse_example(rec), schema)
+        assert set(fast) == set(slow)
+        assert np.array_equal(fast["audio"], slow["audio"]) and np.array_equal(fast["transcript"], slow["transcript"])
+        assert fast["uuid"] == slow["uuid"] == [b"u%d" % n] and fast["none"].size == 0
+        assert n == 0 or fast["audio"].base is not None                     # a view of the record, not a copy
+    two = np.frombuffer(R.encode_example({"uuid": [b"a", b"b"], "audio": np.ones(2, np.float32)}), np.uint8)
+    assert look(two) is None                                                # several bytes values -> general decoder
+    unpacked = np.frombuffer(R._ld(1, R._ld(1, R._ld(1, b"transcript") + R._ld(2, R._ld(3, b"\x08\x07\x08\x81\x01")))), np.uint8)
+    assert look(unpacked) is None and R.parse_example(unpacked)["transcript"][1].tolist() == [7, 129]
+    with pytest.raises(R.TFRecordError):
+        R.FeatureLookup({"audio": R.VarLenInt64})(np.frombuffer(R.encode_example({"audio": np.ones(3, np.float32)}), np.uint8))
+    with pytest.raises(R.TFRecordError):
+        look(np.frombuffer(R.encode_example({"audio": np.ones(3, np.float32)})[:-3], np.uint8))
+    # load_tfrecords takes the general decoder for such records and still yields the same elements
+    p = tmp_path / "mixed.tfrecords"
+    with R.TFRecordWriter(str(p)) as w:
+        w.write(R.encode_example({"uuid": [b"a", b"b"], "audio": np.ones(2, np.float32)}))
+        w.write(R.encode_example({"uuid": "c", "audio": np.zeros(1, np.float32)}))
+    got = list(R.load_tfrecords(str(p), {"audio": R.VarLenFloat, "uuid": R.VarLenString}))
+    assert got[0]["uuid"] == [b"a", b"b"] and got[1]["uuid"] == [b"c"] and got[0]["audio"].tolist() == [1.0, 1.0]
+    # padded rows
+    B, W = 5, 37
+    rows = [torch.randn(int(k)) for k in (0, 1, 20, 37, 36)]
+    dst = torch.full((B, W), 7.0)
+    ptrs = (C.c_void_p * B)(*[r.data_ptr() for r in rows])
+    lens = (C.c_int64 * B)(*[r.numel() for r in rows])
+    lib.b200st_pad_rows_f32(dst.data_ptr(), W, ptrs, lens, B)
+    for j, r in enumerate(rows):
+        assert torch.equal(dst[j, :r.numel()], r) and float(dst[j, r.numel():].abs().sum()) == 0.0
